@@ -1,0 +1,61 @@
+"""Host-side asset decoding for ImageTexture / HdrEnvironment paths.
+
+The reference decodes with the `image` crate (texture.rs:288, hdri_test.rs:45-67).  Here PIL decodes once on
+the host and the *same* texel array is handed to whoever consumes the scene, so decoder differences cannot
+affect parity.  The HDR map of examples/hdri_test.rs (urban_street_04_4k.hdr) is not in the reference
+repository; `synthetic_hdr:<W>x<H>:<seed>` names a procedural stand-in of the same resolution.
+"""
+from __future__ import annotations
+
+import os
+from functools import lru_cache
+
+import numpy as np
+
+
+@lru_cache(maxsize=8)
+def synthetic_hdr(width: int, height: int, seed: int) -> np.ndarray:
+    """Smooth sky gradient + warm ground + one small bright sun disc (~50) + low-amplitude hash noise.
+    Returns (H, W, 3) fp32, row 0 = top (v = 1)."""
+    y = (np.arange(height, dtype=np.float32) + 0.5) / height          # 0 = top
+    x = (np.arange(width, dtype=np.float32) + 0.5) / width
+    elev = (0.5 - y) * np.pi                                             # +pi/2 at top
+    az = (x * 2.0 - 1.0) * np.pi
+    e, a = np.meshgrid(elev, az, indexing="ij")
+    t = np.clip(np.sin(e) * 0.5 + 0.5, 0, 1).astype(np.float32)
+    sky = np.stack([1.0 - 0.6 * t, 1.0 - 0.35 * t, np.ones_like(t)], -1) * (0.6 + 0.8 * t[..., None])
+    ground = np.stack([0.35 + 0 * t, 0.3 + 0 * t, 0.25 + 0 * t], -1)
+    img = np.where((e > 0)[..., None], sky, ground).astype(np.float32)
+    # sun at elevation 40 deg, azimuth 60 deg, angular radius ~1.5 deg
+    se, sa = np.radians(40.0), np.radians(60.0)
+    cosang = np.sin(e) * np.sin(se) + np.cos(e) * np.cos(se) * np.cos(a - sa)
+    img[cosang > np.cos(np.radians(1.5))] = np.array([50.0, 46.0, 40.0], np.float32)
+    # hash noise (deterministic, seed-keyed)
+    ii, jj = np.meshgrid(np.arange(height, dtype=np.uint32), np.arange(width, dtype=np.uint32), indexing="ij")
+    hsh = (ii * np.uint32(73856093)) ^ (jj * np.uint32(19349663)) ^ np.uint32((seed * 83492791) & 0xFFFFFFFF)
+    hsh = (hsh ^ (hsh >> np.uint32(13))) * np.uint32(1274126177)
+    noise = ((hsh >> np.uint32(8)).astype(np.float32) / 16777216.0 - 0.5) * 0.04
+    img *= (1.0 + noise[..., None])
+    return np.ascontiguousarray(img, dtype=np.float32)
+
+
+def load_asset(path: str, kind: str, asset_dir: str | None = None, registry: dict | None = None) -> np.ndarray:
+    """kind = "image" -> (H, W, 4) u8 RGBA   |   kind = "hdr" -> (H, W, 3) fp32."""
+    if registry and path in registry:
+        return registry[path]
+    if path.startswith("synthetic_hdr:"):
+        _, dims, seed = path.split(":")
+        w, h = dims.split("x")
+        return synthetic_hdr(int(w), int(h), int(seed))
+    cands = [path]
+    if asset_dir:
+        cands = [os.path.join(asset_dir, path), os.path.join(asset_dir, os.path.basename(path)), path]
+    for c in cands:
+        if os.path.exists(c):
+            if kind == "hdr":
+                if c.endswith(".npy"):
+                    return np.ascontiguousarray(np.load(c), dtype=np.float32)
+                raise ValueError(f"Radiance .hdr decoding is not implemented (asset {c}); provide a .npy")
+            from PIL import Image
+            return np.ascontiguousarray(np.asarray(Image.open(c).convert("RGBA")), dtype=np.uint8)
+    raise FileNotFoundError(f"asset {path!r} not found (searched {cands})")
