@@ -1,0 +1,105 @@
+// Flattened, pointer-free scene layout shared by the host flattener and the CUDA kernels.
+// See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#else
+struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+struct int4 { int x, y, z, w; };
+struct uchar4 { unsigned char x, y, z, w; };
+typedef unsigned long long cudaTextureObject_t;
+#endif
+
+namespace fw {
+
+enum ShapeKind : int {
+    SH_SPHERE = 0,    // objects/sphere.rs
+    SH_RECT = 1,      // objects/rect.rs      (plane in i0 bits 0-1: 0 XY, 1 XZ, 2 YZ; flip_normal bit 2)
+    SH_RECT3D = 2,    // objects/rect3d.rs    (i0 = first face ShapeRec, i1 = face count)
+    SH_MESH = 3,      // objects/mesh.rs      (i0 = MeshRec index)
+    SH_DISK = 4,      // objects/disk.rs
+    SH_CYLINDER = 5,  // objects/cylinder.rs
+    SH_CONE = 6,      // objects/cone.rs
+    SH_MEDIUM = 7,    // objects/volume.rs    (i0 = inner ShapeRec, f[0] = density)
+};
+enum MatKind : int {  // material.rs; MAT_MISS is a queue id only
+    MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_EMISSIVE = 3, MAT_ISOTROPIC = 4, MAT_MISS = 5,
+    MAT_NUM_QUEUES = 6
+};
+enum TexKind : int { TEX_CONSTANT = 0, TEX_CHECKER = 1, TEX_PERLIN = 2, TEX_TURBULENCE = 3, TEX_MARBLE = 4, TEX_IMAGE = 5 };
+enum EnvKind : int { ENV_COLOR = 0, ENV_SKY = 1, ENV_HDR = 2 };
+
+constexpr int OBJ_KIND_MASK = 0xff;
+constexpr int OBJ_ROTATED = 1 << 8;   // cos_trace < 0.999 (scene.rs:242-246): ray is rotated into object space
+constexpr int OBJ_FLIP = 1 << 9;      // RenderObject.flip_normals (scene.rs:259-261)
+
+struct ShapeRec {  // 48 B
+    int kind, material, i0, i1;
+    float f[8];
+};
+struct MeshRec {  // 32 B
+    int node_root;   // index into nodes[] of this mesh's BVH root
+    int tri_first;   // first triangle slot (triangles are stored in BVH leaf order)
+    int tri_count;
+    int flags;       // bit0 has_normals, bit1 has_uvs
+    int material;
+    int pad[3];
+};
+struct MatRec {  // 32 B
+    int kind, tex;
+    float param, pad0;
+    float albedo[3], pad1;
+};
+struct TexRec {  // 32 B
+    int kind, a, b, depth;   // checker: a = odd, b = even; image: a = image index
+    float scale;
+    float color[3];
+};
+struct ImageRec {  // 16 B
+    cudaTextureObject_t tex;  // uchar4 point-sampled, unnormalised coordinates
+    uint32_t w, h;
+};
+struct EnvRec {
+    int kind;
+    uint32_t w, h;
+    int pad;
+    float a[4];               // ColorEnv colour | SkyEnv zenith
+    float b[4];               // SkyEnv horizon
+    cudaTextureObject_t tex;  // HdrEnvironment: float4 point-sampled
+};
+
+// BVH node = 2 x float4:  lo = (min.xyz, asfloat(code)),  hi = (max.xyz, asfloat(count))
+//   code >= 0 : interior, children at nodes code and code+1 (siblings adjacent, 64-byte aligned pair)
+//   code <  0 : leaf; p = ~code, items [p >> 1, (p >> 1) + (p & 1) + 1) of the tree's item list
+//               (1 or 2 items: bvh.rs Leaf / DoubleLeaf)
+struct DeviceScene {
+    const float4* nodes;       // all trees; top-level root at node 0
+    const int* top_items;      // object ids in top-level DFS leaf order (rank = tie-break key, bvh.rs:128,141)
+    const float4* obj_posr;    // per object: (position.xyz, sphere radius or 0)
+    const int4* obj_meta;      // per object: (kind | flags, material, shape index, 0)
+    const float4* obj_rot;     // per object: 3 x float4 = columns of rotation_mat
+    const float4* obj_irot;    // per object: 3 x float4 = columns of inv_rotation_mat
+    const ShapeRec* shapes;
+    const MeshRec* meshes;
+    const float4* tri_verts;   // per triangle slot: 3 x float4 (p0, p1, p2; p0.w = asfloat(original index))
+    const float4* tri_normals; // per triangle slot: 3 x float4 (only for meshes with normals; else unused)
+    const float2* tri_uvs;     // per triangle slot: 3 x float2 (default (0,0),(1,0),(0,1) if the mesh has none)
+    const MatRec* mats;
+    const TexRec* texs;
+    const ImageRec* images;
+    EnvRec env;
+    int n_objects;
+    int n_nodes;
+    int top_root_is_valid;     // 0 if the top-level BVH was not built (linear scenes may still build it)
+    int has_medium;
+};
+
+struct CameraRec {  // camera.rs:7-16
+    float position[3], horizontal[3], vertical[3], lower_left[3], u[3], v[3], w[3];
+    float lens_radius;
+};
+
+}  // namespace fw

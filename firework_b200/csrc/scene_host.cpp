@@ -1,0 +1,727 @@
+#include "scene_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <functional>
+
+#include "yaml_lite.h"
+
+namespace fw {
+
+using fwyaml::Node;
+
+// ------------------------------------------------------------------------------------------------------
+// YAML -> SceneDesc
+// ------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Loader {
+    SceneDesc& sc;
+    std::string err;
+    explicit Loader(SceneDesc& s) : sc(s) {}
+
+    bool fail(const Node* n, const std::string& msg) {
+        if (err.empty()) err = (n ? "line " + std::to_string(n->line) + ": " : std::string()) + msg;
+        return false;
+    }
+    const Node* req(const Node& m, const char* key) {
+        const Node* n = m.get(key);
+        if (!n) fail(&m, std::string("missing field `") + key + "`");
+        return n;
+    }
+    bool as_f32(const Node* n, float& out) {
+        if (!n) return false;
+        if (n->kind != Node::SCALAR) return fail(n, "expected a number");
+        const std::string& s = n->scalar;
+        if (s == ".nan" || s == ".NaN") { out = NAN; return true; }
+        if (s == ".inf" || s == "+.inf") { out = INFINITY; return true; }
+        if (s == "-.inf") { out = -INFINITY; return true; }
+        char* end = nullptr;
+        double d = strtod(s.c_str(), &end);
+        if (end == s.c_str() || *end) return fail(n, "invalid number `" + s + "`");
+        out = (float)d;
+        return true;
+    }
+    bool as_u64(const Node* n, uint64_t& out) {
+        if (!n) return false;
+        if (n->kind != Node::SCALAR) return fail(n, "expected an integer");
+        const std::string& s = n->scalar;
+        char* end = nullptr;
+        if (!s.empty() && s[0] == '-') return fail(n, "expected a non-negative integer, got `" + s + "`");
+        unsigned long long v = strtoull(s.c_str(), &end, 10);
+        if (end == s.c_str() || *end) return fail(n, "invalid integer `" + s + "`");
+        out = v;
+        return true;
+    }
+    bool as_int(const Node* n, int& out) {
+        uint64_t v;
+        if (!as_u64(n, v)) return false;
+        if (v > 0x7fffffffu) return fail(n, "integer out of range");
+        out = (int)v;
+        return true;
+    }
+    bool as_bool(const Node* n, bool& out) {
+        if (!n) return false;
+        if (n->kind == Node::SCALAR && (n->scalar == "true" || n->scalar == "false")) {
+            out = n->scalar == "true";
+            return true;
+        }
+        return fail(n, "expected true/false");
+    }
+    bool as_str(const Node* n, std::string& out) {
+        if (!n) return false;
+        if (n->kind != Node::SCALAR) return fail(n, "expected a string");
+        out = n->scalar;
+        return true;
+    }
+    bool as_v3(const Node* n, float out[3]) {
+        if (!n) return false;
+        if (n->kind != Node::MAP) return fail(n, "expected {x, y, z}");
+        return as_f32(req(*n, "x"), out[0]) && as_f32(req(*n, "y"), out[1]) && as_f32(req(*n, "z"), out[2]);
+    }
+    bool as_v2(const Node* n, float out[2]) {
+        if (!n) return false;
+        if (n->kind != Node::MAP) return fail(n, "expected {x, y}");
+        return as_f32(req(*n, "x"), out[0]) && as_f32(req(*n, "y"), out[1]);
+    }
+    int add_asset(const std::string& path, int kind) {
+        for (size_t i = 0; i < sc.assets.size(); ++i)
+            if (sc.assets[i].path == path && sc.assets[i].kind == kind) return (int)i;
+        AssetDesc a;
+        a.path = path;
+        a.kind = kind;
+        sc.assets.push_back(std::move(a));
+        return (int)sc.assets.size() - 1;
+    }
+
+    // texture.rs — returns texture index or -1
+    int texture(const Node* n) {
+        if (!n) return -1;
+        if (n->kind != Node::MAP) { fail(n, "expected a texture mapping"); return -1; }
+        std::string tag;
+        if (!as_str(req(*n, "texture"), tag)) return -1;
+        TexRec t;
+        memset(&t, 0, sizeof(t));
+        if (tag == "ConstantTexture") {
+            t.kind = TEX_CONSTANT;
+            if (!as_v3(req(*n, "color"), t.color)) return -1;
+        } else if (tag == "CheckerTexture") {
+            t.kind = TEX_CHECKER;
+            t.a = texture(req(*n, "odd"));
+            t.b = texture(req(*n, "even"));
+            if (t.a < 0 || t.b < 0) return -1;
+            if (!as_f32(req(*n, "scale"), t.scale)) return -1;
+        } else if (tag == "PerlinNoiseTexture") {
+            t.kind = TEX_PERLIN;
+            if (!as_f32(req(*n, "scale"), t.scale)) return -1;
+        } else if (tag == "TurbulenceTexture" || tag == "MarbleTexture") {
+            t.kind = tag == "TurbulenceTexture" ? TEX_TURBULENCE : TEX_MARBLE;
+            uint64_t d;
+            if (!as_u64(req(*n, "depth"), d) || !as_f32(req(*n, "scale"), t.scale)) return -1;
+            t.depth = (int)std::min<uint64_t>(d, 1u << 20);
+        } else if (tag == "ImageTexture") {
+            t.kind = TEX_IMAGE;
+            std::string path;
+            if (!as_str(req(*n, "value"), path)) return -1;
+            t.a = add_asset(path, 0);
+        } else {
+            fail(n, "unknown texture tag `" + tag + "`");
+            return -1;
+        }
+        sc.texs.push_back(t);
+        return (int)sc.texs.size() - 1;
+    }
+
+    // material.rs
+    bool material(const Node& n) {
+        std::string tag;
+        if (!as_str(req(n, "material"), tag)) return false;
+        MatRec m;
+        memset(&m, 0, sizeof(m));
+        m.tex = -1;
+        if (tag == "LambertianMat" || tag == "EmissiveMat") {
+            m.kind = tag == "LambertianMat" ? MAT_LAMBERTIAN : MAT_EMISSIVE;
+            m.tex = texture(req(n, "albedo"));
+            if (m.tex < 0) return false;
+        } else if (tag == "IsotropicMat") {
+            m.kind = MAT_ISOTROPIC;
+            m.tex = texture(req(n, "texture"));
+            if (m.tex < 0) return false;
+        } else if (tag == "MetalMat") {
+            m.kind = MAT_METAL;
+            if (!as_v3(req(n, "albedo"), m.albedo) || !as_f32(req(n, "roughness"), m.param)) return false;
+        } else if (tag == "DielectricMat") {
+            m.kind = MAT_DIELECTRIC;
+            if (!as_f32(req(n, "ref_idx"), m.param)) return false;
+        } else {
+            return fail(&n, "unknown material tag `" + tag + "`");
+        }
+        sc.mats.push_back(m);
+        return true;
+    }
+
+    bool rect_fields(const Node& n, int plane, ShapeRec& s) {
+        memset(&s, 0, sizeof(s));
+        s.kind = SH_RECT;
+        float mn[2], mx[2];
+        bool flip;
+        if (!as_v2(req(n, "min"), mn) || !as_v2(req(n, "max"), mx) || !as_f32(req(n, "k"), s.f[4]) ||
+            !as_bool(req(n, "flip_normal"), flip) || !as_int(req(n, "material"), s.material))
+            return false;
+        s.f[0] = mn[0]; s.f[1] = mn[1]; s.f[2] = mx[0]; s.f[3] = mx[1];
+        s.i0 = plane | (flip ? 4 : 0);
+        return true;
+    }
+    static int plane_of(const std::string& tag) {
+        if (tag == "XY" || tag == "XYRect") return 0;
+        if (tag == "XZ" || tag == "XZRect") return 1;
+        if (tag == "YZ" || tag == "YZRect") return 2;
+        return -1;
+    }
+
+    // objects/*.rs — returns shape index or -1
+    int shape(const Node* np) {
+        if (!np) return -1;
+        const Node& n = *np;
+        if (n.kind != Node::MAP) { fail(np, "expected a shape mapping"); return -1; }
+        std::string tag;
+        if (!as_str(req(n, "object_type"), tag)) return -1;
+        ShapeRec s;
+        memset(&s, 0, sizeof(s));
+        if (tag == "Sphere") {
+            s.kind = SH_SPHERE;
+            if (!as_f32(req(n, "radius"), s.f[0]) || !as_int(req(n, "material"), s.material)) return -1;
+        } else if (plane_of(tag) >= 0) {
+            if (!rect_fields(n, plane_of(tag), s)) return -1;
+        } else if (tag == "Rect3d") {
+            s.kind = SH_RECT3D;
+            float pos[3], size[3];
+            if (!as_v3(req(n, "pos"), pos) || !as_v3(req(n, "size"), size)) return -1;
+            memcpy(&s.f[0], pos, 12);
+            memcpy(&s.f[3], size, 12);
+            const Node* faces = req(n, "faces");
+            if (!faces) return -1;
+            if (faces->kind != Node::SEQ && !faces->is_null()) { fail(faces, "expected a list of faces"); return -1; }
+            std::vector<ShapeRec> fr;
+            for (const Node& f : faces->seq) {
+                // enum Rect { XY(..), XZ(..), YZ(..) } — externally tagged: {XY: {...}}
+                if (f.kind != Node::MAP || f.map.size() != 1) { fail(&f, "expected {XY|XZ|YZ: rect}"); return -1; }
+                int plane = plane_of(f.map[0].first);
+                if (plane < 0) { fail(&f, "unknown Rect variant `" + f.map[0].first + "`"); return -1; }
+                ShapeRec r;
+                if (f.map[0].second.kind != Node::MAP) { fail(&f, "expected rect fields"); return -1; }
+                if (!rect_fields(f.map[0].second, plane, r)) return -1;
+                fr.push_back(r);
+            }
+            s.i0 = (int)sc.shapes.size();
+            s.i1 = (int)fr.size();
+            s.material = fr.empty() ? 0 : fr[0].material;
+            for (auto& r : fr) sc.shapes.push_back(r);
+        } else if (tag == "TriangleMesh") {
+            s.kind = SH_MESH;
+            MeshDesc m;
+            const Node* idx = req(n, "indicies");
+            const Node* verts = req(n, "verts");
+            if (!idx || !verts) return -1;
+            if (idx->kind != Node::SEQ || verts->kind != Node::SEQ) { fail(&n, "mesh needs indicies and verts lists"); return -1; }
+            m.indicies.reserve(idx->seq.size());
+            for (const Node& i : idx->seq) {
+                uint64_t v;
+                if (!as_u64(&i, v)) return -1;
+                m.indicies.push_back((uint32_t)v);
+            }
+            m.verts.reserve(verts->seq.size());
+            for (const Node& v : verts->seq) {
+                float p[3];
+                if (!as_v3(&v, p)) return -1;
+                m.verts.push_back(V3{p[0], p[1], p[2]});
+            }
+            const Node* nn = n.get("normals");
+            if (nn && nn->kind == Node::SEQ) {
+                m.has_normals = true;
+                for (const Node& v : nn->seq) {
+                    float p[3];
+                    if (!as_v3(&v, p)) return -1;
+                    m.normals.push_back(V3{p[0], p[1], p[2]});
+                }
+                if (m.normals.size() != m.verts.size()) { fail(nn, "TriangleMesh: normals.len() must equal verts.len()"); return -1; }
+            }
+            const Node* un = n.get("uvs");
+            if (un && un->kind == Node::SEQ) {
+                m.has_uvs = true;
+                for (const Node& v : un->seq) {
+                    float p[2];
+                    if (!as_v2(&v, p)) return -1;
+                    m.uvs.push_back(p[0]);
+                    m.uvs.push_back(p[1]);
+                }
+                if (m.uvs.size() != 2 * m.verts.size()) { fail(un, "TriangleMesh: uvs.len() must equal verts.len()"); return -1; }
+            }
+            if (!as_int(req(n, "material"), m.material)) return -1;
+            if (m.indicies.size() < 3) { fail(&n, "TriangleMesh with no triangles"); return -1; }
+            for (uint32_t i : m.indicies)
+                if (i >= m.verts.size()) { fail(idx, "TriangleMesh index out of range"); return -1; }
+            s.material = m.material;
+            s.i0 = (int)sc.meshes.size();
+            sc.meshes.push_back(std::move(m));
+        } else if (tag == "Disk") {
+            s.kind = SH_DISK;
+            if (!as_f32(req(n, "radius"), s.f[0]) || !as_f32(req(n, "phi_max"), s.f[1]) ||
+                !as_f32(req(n, "inner_radius"), s.f[2]) || !as_int(req(n, "material"), s.material))
+                return -1;
+        } else if (tag == "Cylinder") {
+            s.kind = SH_CYLINDER;
+            if (!as_f32(req(n, "radius"), s.f[0]) || !as_f32(req(n, "height"), s.f[1]) ||
+                !as_f32(req(n, "max_phi"), s.f[2]) || !as_int(req(n, "material"), s.material))
+                return -1;
+        } else if (tag == "Cone") {
+            s.kind = SH_CONE;
+            if (!as_f32(req(n, "radius"), s.f[0]) || !as_f32(req(n, "height"), s.f[1]) ||
+                !as_int(req(n, "material"), s.material))
+                return -1;
+        } else if (tag == "ConstantMedium") {
+            s.kind = SH_MEDIUM;
+            int inner = shape(req(n, "obj"));
+            if (inner < 0) return -1;
+            if (sc.shapes[inner].kind == SH_MEDIUM) { fail(&n, "nested ConstantMedium is not supported"); return -1; }
+            s.i0 = inner;
+            if (!as_f32(req(n, "density"), s.f[0]) || !as_int(req(n, "material"), s.material)) return -1;
+        } else {
+            fail(&n, "unknown object_type `" + tag + "`");
+            return -1;
+        }
+        sc.shapes.push_back(s);
+        return (int)sc.shapes.size() - 1;
+    }
+
+    bool object(const Node& n) {
+        if (n.kind != Node::MAP) return fail(&n, "expected a render object mapping");
+        ObjectDesc o;
+        o.shape = shape(req(n, "obj"));
+        if (o.shape < 0) return false;
+        float p[3];
+        if (!as_v3(req(n, "position"), p)) return false;
+        o.position = V3{p[0], p[1], p[2]};
+        const Node* rot = req(n, "rotation");
+        if (!rot) return false;
+        const Node* bv = req(*rot, "bv");
+        if (!bv) return false;
+        if (!as_f32(req(*rot, "s"), o.rotor[0]) || !as_f32(req(*bv, "xy"), o.rotor[1]) ||
+            !as_f32(req(*bv, "xz"), o.rotor[2]) || !as_f32(req(*bv, "yz"), o.rotor[3]))
+            return false;
+        if (!as_bool(req(n, "flip_normals"), o.flip_normals)) return false;
+        sc.objects.push_back(o);
+        return true;
+    }
+
+    bool run(const Node& root) {
+        if (root.kind != Node::MAP) return fail(&root, "scene document must be a mapping");
+        const Node* mats = req(root, "materials");
+        const Node* objs = req(root, "render_objects");
+        const Node* env = req(root, "environment");
+        if (!mats || !objs || !env) return false;
+        if (mats->kind == Node::SEQ)
+            for (const Node& m : mats->seq)
+                if (!material(m)) return false;
+        if (objs->kind == Node::SEQ)
+            for (const Node& o : objs->seq)
+                if (!object(o)) return false;
+        // validate material indices (the reference would panic on use: scene.rs:86)
+        for (const ShapeRec& s : sc.shapes)
+            if (s.kind != SH_RECT3D && (s.material < 0 || s.material >= (int)sc.mats.size()))
+                return fail(objs, "shape refers to material " + std::to_string(s.material) + " but the scene has " +
+                                      std::to_string(sc.mats.size()));
+        std::string tag;
+        if (env->kind != Node::MAP || !as_str(req(*env, "environment"), tag)) return fail(env, "bad environment");
+        if (tag == "ColorEnv") {
+            sc.env_kind = ENV_COLOR;
+            if (!as_v3(req(*env, "color"), sc.env_a)) return false;
+        } else if (tag == "SkyEnv") {
+            sc.env_kind = ENV_SKY;
+            if (!as_v3(req(*env, "zenith_color"), sc.env_a) || !as_v3(req(*env, "horizon_color"), sc.env_b)) return false;
+        } else if (tag == "HdrEnvironment") {
+            sc.env_kind = ENV_HDR;
+            std::string path;
+            if (!as_str(req(*env, "value"), path)) return false;
+            sc.env_asset = add_asset(path, 1);
+        } else {
+            return fail(env, "unknown environment tag `" + tag + "`");
+        }
+        return true;
+    }
+};
+
+}  // namespace
+
+bool load_scene_yaml(const char* text, size_t len, SceneDesc& out, std::string& err) {
+    Node root;
+    if (!fwyaml::parse(text, len, root, err)) return false;
+    out = SceneDesc();
+    Loader ld(out);
+    if (!ld.run(root)) {
+        err = ld.err.empty() ? "invalid scene document" : ld.err;
+        return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// f32 helpers with the reference's operation order (ultraviolet Vec3 / Mat3, aabb.rs)
+// ------------------------------------------------------------------------------------------------------
+static inline V3 vmin(V3 a, V3 b) { return V3{fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)}; }
+static inline V3 vmax(V3 a, V3 b) { return V3{fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)}; }
+static inline Box box_expand(const Box& a, const Box& b) { return Box{vmin(a.mn, b.mn), vmax(a.mx, b.mx)}; }  // aabb.rs:52
+static inline float comp(const V3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+static inline V3 box_center(const Box& b) {  // aabb.rs:59-61
+    return V3{0.5f * b.mn.x + 0.5f * b.mx.x, 0.5f * b.mn.y + 0.5f * b.mx.y, 0.5f * b.mn.z + 0.5f * b.mx.z};
+}
+
+// ------------------------------------------------------------------------------------------------------
+// BVH build: bvh.rs:21-71
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct BuildNode {
+    Box box;
+    int left = -1, right = -1;  // interior
+    int first = -1, count = 0;  // leaf: range in the ordered item list
+    int depth = 0;
+};
+struct Builder {
+    const std::vector<Box>& boxes;
+    std::vector<V3> centers;
+    std::vector<int> order;
+    std::vector<BuildNode> nodes;
+    bool nan = false;
+    explicit Builder(const std::vector<Box>& b) : boxes(b) {
+        centers.reserve(b.size());
+        for (const Box& x : b) centers.push_back(box_center(x));
+        order.resize(b.size());
+        for (size_t i = 0; i < b.size(); ++i) order[i] = (int)i;
+    }
+    int build(int lo, int n, int depth) {
+        int axis = depth % 3;
+        for (int i = lo; i < lo + n; ++i)
+            if (std::isnan(comp(centers[order[i]], axis))) nan = true;  // bvh.rs:34 would panic
+        std::stable_sort(order.begin() + lo, order.begin() + lo + n,
+                         [&](int a, int b) { return comp(centers[a], axis) < comp(centers[b], axis); });
+        int id = (int)nodes.size();
+        nodes.emplace_back();
+        nodes[id].depth = depth;
+        if (n == 1) {
+            nodes[id].box = boxes[order[lo]];
+            nodes[id].first = lo;
+            nodes[id].count = 1;
+        } else if (n == 2) {
+            nodes[id].box = box_expand(boxes[order[lo]], boxes[order[lo + 1]]);
+            nodes[id].first = lo;
+            nodes[id].count = 2;
+        } else {
+            int half = n / 2;
+            int l = build(lo, half, depth + 1);
+            int r = build(lo + half, n - half, depth + 1);
+            nodes[id].left = l;
+            nodes[id].right = r;
+            nodes[id].box = box_expand(nodes[l].box, nodes[r].box);
+        }
+        return id;
+    }
+};
+static inline float as_float(int i) {
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
+}  // namespace
+
+bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& err) {
+    out = FlatBVH();
+    if (item_boxes.empty()) {
+        err = "cannot build a BVH over zero items (the reference recurses forever: bvh.rs:59)";
+        return false;
+    }
+    Builder b(item_boxes);
+    b.nodes.reserve(item_boxes.size() * 2);
+    int root = b.build(0, (int)item_boxes.size(), 0);
+    if (b.nan) {
+        err = "Float comparison failed in BVH constructor (NaN centroid; bvh.rs:34)";
+        return false;
+    }
+    out.items = b.order;
+    // Breadth-first layout: root at 0, node 1 is padding, sibling pairs at even indices.
+    out.nodes.assign(4, float4{0, 0, 0, 0});
+    std::deque<std::pair<int, int>> q;  // (build node, flat index)
+    q.emplace_back(root, 0);
+    int next = 2;
+    while (!q.empty()) {
+        auto [bn, fi] = q.front();
+        q.pop_front();
+        const BuildNode& n = b.nodes[bn];
+        out.max_depth = std::max(out.max_depth, n.depth);
+        int a, bb;
+        if (n.count > 0) {
+            a = ~(n.first * 2 + (n.count - 1));  // leaf code: items [first, first + count), count in {1, 2}
+            bb = n.count;
+        } else {
+            a = next;
+            bb = 0;
+            next += 2;
+            if ((int)out.nodes.size() < 2 * next) out.nodes.resize(2 * (size_t)next, float4{0, 0, 0, 0});
+            q.emplace_back(n.left, a);
+            q.emplace_back(n.right, a + 1);
+        }
+        out.nodes[2 * fi] = float4{n.box.mn.x, n.box.mn.y, n.box.mn.z, as_float(a)};
+        out.nodes[2 * fi + 1] = float4{n.box.mx.x, n.box.mx.y, n.box.mx.z, as_float(bb)};
+    }
+    // padding node 1: an empty leaf with an inverted box (never reachable, never hit)
+    out.nodes[2] = float4{INFINITY, INFINITY, INFINITY, as_float(~0)};
+    out.nodes[3] = float4{-INFINITY, -INFINITY, -INFINITY, as_float(0)};
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Flattening
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct M3 {
+    V3 c[3];
+};
+static inline V3 mat_mul(const M3& m, V3 v) {  // ultraviolet Mat3 * Vec3
+    return V3{m.c[0].x * v.x + m.c[1].x * v.y + m.c[2].x * v.z, m.c[0].y * v.x + m.c[1].y * v.y + m.c[2].y * v.z,
+              m.c[0].z * v.x + m.c[1].z * v.y + m.c[2].z * v.z};
+}
+// ultraviolet Rotor3::into_matrix (see DESIGN.md "un-vendored arithmetic")
+static M3 rotor_matrix(float s, float xy, float xz, float yz) {
+    float s2 = s * s, bxy2 = xy * xy, bxz2 = xz * xz, byz2 = yz * yz;
+    float s_bxy = s * xy, s_bxz = s * xz, s_byz = s * yz;
+    float bxz_byz = xz * yz, bxy_byz = xy * yz, bxy_bxz = xy * xz;
+    const float two = 2.0f;
+    M3 m;
+    m.c[0] = V3{s2 - bxy2 - bxz2 + byz2, -two * (bxz_byz + s_bxy), two * (bxy_byz - s_bxz)};
+    m.c[1] = V3{two * (s_bxy - bxz_byz), s2 - bxy2 + bxz2 - byz2, -two * (s_byz + bxy_bxz)};
+    m.c[2] = V3{two * (s_bxz + bxy_byz), two * (s_byz - bxy_bxz), s2 + bxy2 - bxz2 - byz2};
+    return m;
+}
+
+// mesh.rs:221-242
+static Box triangle_box(V3 p0, V3 p1, V3 p2) {
+    Box b{vmin(p0, p1), vmax(p0, p1)};
+    b.mn = vmin(b.mn, p2);
+    b.mx = vmax(b.mx, p2);
+    V3 size{fabsf(b.mx.x - b.mn.x), fabsf(b.mx.y - b.mn.y), fabsf(b.mx.z - b.mn.z)};
+    if (size.x < 0.001f) { b.mn.x -= 0.001f; b.mx.x += 0.001f; }
+    if (size.y < 0.001f) { b.mn.y -= 0.001f; b.mx.y += 0.001f; }
+    if (size.z < 0.001f) { b.mn.z -= 0.001f; b.mx.z += 0.001f; }
+    return b;
+}
+}  // namespace
+
+bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
+    out = HostFlat();
+    if (desc.objects.empty()) {
+        err = "No render objects added to scene! (scene.rs:161)";
+        return false;
+    }
+    out.shapes = desc.shapes;
+    out.mats = desc.mats;
+    out.texs = desc.texs;
+
+    // Top-level tree occupies the front of nodes[]; it is appended after its size is known, so build
+    // meshes into a side buffer first.
+    std::vector<float4> mesh_nodes;
+    std::vector<Box> mesh_root_box(desc.meshes.size());
+    std::vector<int> mesh_node_root(desc.meshes.size());
+    for (size_t mi = 0; mi < desc.meshes.size(); ++mi) {
+        const MeshDesc& m = desc.meshes[mi];
+        size_t ntri = m.indicies.size() / 3;
+        std::vector<Box> tb(ntri);
+        for (size_t t = 0; t < ntri; ++t)
+            tb[t] = triangle_box(m.verts[m.indicies[3 * t]], m.verts[m.indicies[3 * t + 1]], m.verts[m.indicies[3 * t + 2]]);
+        FlatBVH bvh;
+        if (!build_bvh(tb, bvh, err)) return false;
+        MeshRec rec;
+        memset(&rec, 0, sizeof(rec));
+        rec.node_root = (int)(mesh_nodes.size() / 2);  // relative; rebased below
+        rec.tri_first = (int)(out.tri_verts.size() / 3);
+        rec.tri_count = (int)ntri;
+        rec.flags = (m.has_normals ? 1 : 0) | (m.has_uvs ? 2 : 0);
+        rec.material = m.material;
+        mesh_node_root[mi] = rec.node_root;
+        // nodes: child indices are tree-local; rebase interior links later (after top-level size is known)
+        mesh_nodes.insert(mesh_nodes.end(), bvh.nodes.begin(), bvh.nodes.end());
+        const float4& rlo = bvh.nodes[0];
+        const float4& rhi = bvh.nodes[1];
+        mesh_root_box[mi] = Box{V3{rlo.x, rlo.y, rlo.z}, V3{rhi.x, rhi.y, rhi.z}};
+        for (size_t slot = 0; slot < ntri; ++slot) {
+            int t = bvh.items[slot];
+            uint32_t i0 = m.indicies[3 * t], i1 = m.indicies[3 * t + 1], i2 = m.indicies[3 * t + 2];
+            V3 p0 = m.verts[i0], p1 = m.verts[i1], p2 = m.verts[i2];
+            out.tri_verts.push_back(float4{p0.x, p0.y, p0.z, as_float(t)});
+            out.tri_verts.push_back(float4{p1.x, p1.y, p1.z, 0});
+            out.tri_verts.push_back(float4{p2.x, p2.y, p2.z, 0});
+            if (m.has_normals) {
+                V3 n0 = m.normals[i0], n1 = m.normals[i1], n2 = m.normals[i2];
+                out.tri_normals.push_back(float4{n0.x, n0.y, n0.z, 0});
+                out.tri_normals.push_back(float4{n1.x, n1.y, n1.z, 0});
+                out.tri_normals.push_back(float4{n2.x, n2.y, n2.z, 0});
+            } else {
+                for (int k = 0; k < 3; ++k) out.tri_normals.push_back(float4{0, 0, 0, 0});
+            }
+            if (m.has_uvs) {
+                out.tri_uvs.push_back(float2{m.uvs[2 * i0], m.uvs[2 * i0 + 1]});
+                out.tri_uvs.push_back(float2{m.uvs[2 * i1], m.uvs[2 * i1 + 1]});
+                out.tri_uvs.push_back(float2{m.uvs[2 * i2], m.uvs[2 * i2 + 1]});
+            } else {  // mesh.rs:108
+                out.tri_uvs.push_back(float2{0, 0});
+                out.tri_uvs.push_back(float2{1, 0});
+                out.tri_uvs.push_back(float2{0, 1});
+            }
+        }
+        out.meshes.push_back(rec);
+    }
+
+    // shape bounding boxes (object space)
+    std::function<bool(int, Box&)> shape_box = [&](int si, Box& b) -> bool {
+        const ShapeRec& s = desc.shapes[si];
+        switch (s.kind) {
+            case SH_SPHERE: {  // sphere.rs:62-64
+                float r = s.f[0];
+                b = Box{V3{-1.0f * r, -1.0f * r, -1.0f * r}, V3{1.0f * r, 1.0f * r, 1.0f * r}};
+                return true;
+            }
+            case SH_RECT: {  // rect.rs:75-86
+                static const int A1[3] = {0, 0, 1}, A2[3] = {1, 2, 2}, AK[3] = {2, 1, 0};
+                int p = s.i0 & 3;
+                float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+                lo[A1[p]] = s.f[0]; lo[A2[p]] = s.f[1]; lo[AK[p]] = s.f[4] - 0.01f;
+                hi[A1[p]] = s.f[2]; hi[A2[p]] = s.f[3]; hi[AK[p]] = s.f[4] + 0.01f;
+                b = Box{V3{lo[0], lo[1], lo[2]}, V3{hi[0], hi[1], hi[2]}};
+                return true;
+            }
+            case SH_RECT3D:  // rect3d.rs:102-104
+                b = Box{V3{s.f[0], s.f[1], s.f[2]}, V3{s.f[0] + s.f[3], s.f[1] + s.f[4], s.f[2] + s.f[5]}};
+                return true;
+            case SH_MESH:
+                b = mesh_root_box[s.i0];
+                return true;
+            case SH_DISK:  // disk.rs:85-90 (degenerate box preserved)
+                b = Box{V3{-s.f[0], 0.0f, s.f[0]}, V3{-s.f[0], 0.001f, s.f[0]}};
+                return true;
+            case SH_CYLINDER:  // cylinder.rs:92-97
+            case SH_CONE:      // cone.rs:90-95
+                b = Box{V3{-s.f[0], 0.0f, -s.f[0]}, V3{s.f[0], s.f[1], s.f[0]}};
+                return true;
+            case SH_MEDIUM:  // volume.rs:84-86
+                return shape_box(s.i0, b);
+        }
+        err = "bad shape kind";
+        return false;
+    };
+
+    size_t nobj = desc.objects.size();
+    out.obj_aabb.resize(nobj);
+    for (size_t i = 0; i < nobj; ++i) {
+        const ObjectDesc& o = desc.objects[i];
+        const ShapeRec& s = desc.shapes[o.shape];
+        M3 R = rotor_matrix(o.rotor[0], o.rotor[1], o.rotor[2], o.rotor[3]);       // scene.rs:284
+        M3 Ri = rotor_matrix(o.rotor[0], -o.rotor[1], -o.rotor[2], -o.rotor[3]);   // scene.rs:285 (reversed)
+        float trace = R.c[0].x + R.c[1].y + R.c[2].z;
+        float cos_trace = 0.5f * (trace - 1.0f);
+        bool rotated = cos_trace < 0.999f;
+        Box bbox;
+        if (!shape_box(o.shape, bbox)) return false;
+        Box rb;
+        if (rotated) {  // scene.rs:186-208
+            V3 mn{10e9f * 1.0f, 10e9f * 1.0f, 10e9f * 1.0f};
+            V3 mx{-10e9f * 1.0f, -10e9f * 1.0f, -10e9f * 1.0f};
+            for (int a = 0; a < 2; ++a)
+                for (int bq = 0; bq < 2; ++bq)
+                    for (int c = 0; c < 2; ++c) {
+                        V3 corner{a == 0 ? bbox.mn.x : bbox.mx.x, bq == 0 ? bbox.mn.y : bbox.mx.y, c == 0 ? bbox.mn.z : bbox.mx.z};
+                        V3 np = mat_mul(R, corner);
+                        mx = V3{fmaxf(np.x, mx.x), fmaxf(np.y, mx.y), fmaxf(np.z, mx.z)};
+                        mn = V3{fminf(np.x, mn.x), fminf(np.y, mn.y), fminf(np.z, mn.z)};
+                    }
+            rb = Box{mn, mx};
+        } else {
+            rb = bbox;
+        }
+        out.obj_aabb[i] = Box{V3{rb.mn.x + o.position.x, rb.mn.y + o.position.y, rb.mn.z + o.position.z},
+                              V3{rb.mx.x + o.position.x, rb.mx.y + o.position.y, rb.mx.z + o.position.z}};
+        int flags = s.kind | (rotated ? OBJ_ROTATED : 0) | (o.flip_normals ? OBJ_FLIP : 0);
+        out.obj_posr.push_back(float4{o.position.x, o.position.y, o.position.z, s.kind == SH_SPHERE ? s.f[0] : 0.0f});
+        out.obj_meta.push_back(int4{flags, s.material, o.shape, 0});
+        for (int c = 0; c < 3; ++c) {
+            out.obj_rot.push_back(float4{R.c[c].x, R.c[c].y, R.c[c].z, 0});
+            out.obj_irot.push_back(float4{Ri.c[c].x, Ri.c[c].y, Ri.c[c].z, 0});
+        }
+        if (s.kind == SH_MEDIUM) out.has_medium = true;
+    }
+
+    // top-level BVH (bvh.rs:79-98), always built: linear-scan renders simply do not use it
+    FlatBVH top;
+    if (!build_bvh(out.obj_aabb, top, err)) return false;
+    out.top_items = top.items;
+    out.top_depth = top.max_depth;
+    out.top_nodes = (int)(top.nodes.size() / 2);
+    out.nodes = top.nodes;
+    if ((out.nodes.size() / 2) % 2) {  // keep every tree's root on an even node index
+        out.nodes.push_back(float4{INFINITY, INFINITY, INFINITY, as_float(~0)});
+        out.nodes.push_back(float4{-INFINITY, -INFINITY, -INFINITY, as_float(0)});
+    }
+    int base = (int)(out.nodes.size() / 2);
+    // append mesh trees, rebasing interior child links and mesh roots
+    size_t start = out.nodes.size();
+    out.nodes.insert(out.nodes.end(), mesh_nodes.begin(), mesh_nodes.end());
+    {
+        // each mesh tree's links are local to that tree: rebase by (base + tree offset)
+        for (size_t mi = 0; mi < out.meshes.size(); ++mi) {
+            int tree_off = mesh_node_root[mi];
+            int tree_end = (mi + 1 < out.meshes.size()) ? mesh_node_root[mi + 1] : (int)(mesh_nodes.size() / 2);
+            for (int n = tree_off; n < tree_end; ++n) {
+                float4& lo = out.nodes[start + 2 * (size_t)n];
+                int a;
+                memcpy(&a, &lo.w, 4);
+                if (a >= 0) {
+                    a += base + tree_off;
+                    lo.w = as_float(a);
+                }
+            }
+            out.meshes[mi].node_root = base + tree_off;
+        }
+    }
+    return true;
+}
+
+// camera.rs:74-107
+CameraRec make_camera(const RenderParamsHost& p) {
+    const float PI_F = 3.14159265358979323846f;
+    auto sub = [](V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; };
+    auto mulf = [](float s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; };
+    auto cross = [](V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; };
+    auto norm = [](V3 a) {
+        float m = sqrtf((a.x * a.x) + (a.y * a.y) + (a.z * a.z));
+        return V3{a.x / m, a.y / m, a.z / m};
+    };
+    V3 cam_pos{p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]}, look_at{p.look_at[0], p.look_at[1], p.look_at[2]};
+    float theta = p.vfov * PI_F / 180.0f;
+    V3 w = norm(sub(cam_pos, look_at));
+    V3 u = norm(cross(V3{0, 1, 0}, w));
+    V3 v = cross(w, u);
+    float half_height = tanf(theta / 2.0f);
+    float half_width = half_height * (float)p.width / (float)p.height;
+    V3 ll = sub(sub(sub(cam_pos, mulf(half_width * p.focus_dist, u)), mulf(half_height * p.focus_dist, v)),
+                V3{w.x * p.focus_dist, w.y * p.focus_dist, w.z * p.focus_dist});
+    V3 hor = mulf(2.0f * half_width * p.focus_dist, u);
+    V3 ver = mulf(2.0f * half_height * p.focus_dist, v);
+    CameraRec c;
+    auto put = [](float* d, V3 s) { d[0] = s.x; d[1] = s.y; d[2] = s.z; };
+    put(c.position, cam_pos); put(c.horizontal, hor); put(c.vertical, ver); put(c.lower_left, ll);
+    put(c.u, u); put(c.v, v); put(c.w, w);
+    c.lens_radius = p.aperture / 2.0f;
+    return c;
+}
+
+}  // namespace fw

@@ -1,0 +1,96 @@
+// Host side of the drop-in boundary: firework serde-YAML scene document -> neutral description ->
+// BVHs built with the reference's split rule -> pointer-free flattened arrays (fw_types.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "fw_types.h"
+
+namespace fw {
+
+struct V3 {
+    float x, y, z;
+};
+struct Box {
+    V3 mn, mx;
+};
+
+struct AssetDesc {
+    std::string path;
+    int kind = 0;  // 0 = RGBA8 image (ImageTexture), 1 = fp32 RGB equirect map (HdrEnvironment)
+    uint32_t w = 0, h = 0;
+    std::vector<uint8_t> rgba;  // kind 0
+    std::vector<float> rgb;     // kind 1
+    bool provided = false;
+};
+
+struct MeshDesc {  // objects/mesh.rs:12-19
+    std::vector<uint32_t> indicies;
+    std::vector<V3> verts;
+    bool has_normals = false, has_uvs = false;
+    std::vector<V3> normals;
+    std::vector<float> uvs;  // 2 per vertex
+    int material = 0;
+};
+
+struct ObjectDesc {  // scene.rs:268-277
+    int shape = 0;
+    V3 position{0, 0, 0};
+    float rotor[4] = {1, 0, 0, 0};  // s, xy, xz, yz
+    bool flip_normals = false;
+};
+
+struct SceneDesc {
+    std::vector<TexRec> texs;
+    std::vector<MatRec> mats;
+    std::vector<ShapeRec> shapes;
+    std::vector<MeshDesc> meshes;
+    std::vector<ObjectDesc> objects;
+    std::vector<AssetDesc> assets;
+    int env_kind = ENV_COLOR;
+    float env_a[3] = {0, 0, 0}, env_b[3] = {0, 0, 0};
+    int env_asset = -1;
+};
+
+// Parses a firework scene document (the output of serde_yaml::to_string(&Scene)). Unknown tags are errors.
+bool load_scene_yaml(const char* text, size_t len, SceneDesc& out, std::string& err);
+
+// One BVH in flattened form (see fw_types.h for the node encoding).
+struct FlatBVH {
+    std::vector<float4> nodes;   // 2 per node, indices local to this tree (root = node 0, node 1 = padding)
+    std::vector<int> items;      // item ids in DFS leaf order
+    int max_depth = 0;
+};
+// The reference's median split (bvh.rs:21-71): stable sort on centroid[depth % 3], leaves of 1 or 2.
+bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& err);
+
+struct HostFlat {
+    std::vector<float4> nodes;
+    std::vector<int> top_items;
+    std::vector<float4> obj_posr;
+    std::vector<int4> obj_meta;
+    std::vector<float4> obj_rot, obj_irot;
+    std::vector<Box> obj_aabb;  // world boxes (scene.rs:167-212), kept for tests / stats
+    std::vector<ShapeRec> shapes;
+    std::vector<MeshRec> meshes;
+    std::vector<float4> tri_verts, tri_normals;
+    std::vector<float2> tri_uvs;
+    std::vector<MatRec> mats;
+    std::vector<TexRec> texs;
+    int top_depth = 0;
+    int top_nodes = 0;
+    bool has_medium = false;
+};
+bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err);
+
+struct RenderParamsHost {
+    uint32_t width, height, samples, sample_begin, sample_count, use_bvh;
+    float gamma;
+    float cam_pos[3], look_at[3];
+    float vfov, aperture, focus_dist;
+    uint64_t seed;
+};
+CameraRec make_camera(const RenderParamsHost& p);
+
+}  // namespace fw

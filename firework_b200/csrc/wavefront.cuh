@@ -1,0 +1,340 @@
+// Wavefront path tracer kernels: raygen -> [extend -> miss / shade_<material>]* -> accumulate -> resolve.
+// Iterative form of render.rs:12-33 `color()` (depth cap 10) inside render.rs:163-196 `render_pixel`.
+//
+// Path p of a batch covers pixel  pix0 + p % npix  and sample  s0 + p / npix  (implicit mapping: no id arrays).
+// Per-path state lives in HBM as SoA float4 streams; per-bounce queues hold path ids, compacted with
+// warp ballot / popc so that one atomicAdd per warp per queue reserves the slots.
+#pragma once
+#include "intersect.cuh"
+#include "shade.cuh"
+
+namespace fw {
+
+constexpr int FW_MAX_DEPTH = 10;          // render.rs:21  `depth < 10`
+constexpr int FW_COUNTERS_PER_BOUNCE = 8; // [0..5] material queues (MatKind), [6] next extend queue, [7] spare
+
+struct PathState {
+    float4* ray_o;     // [cap] origin.xyz
+    float4* ray_d;     // [cap] direction.xyz (never normalised: ray.rs)
+    float4* hit_p;     // [cap] point.xyz, t
+    float4* hit_n;     // [cap] normal.xyz, asfloat(material)
+    float2* hit_uv;    // [cap]
+    float4* atten;     // [FW_MAX_DEPTH][cap] attenuation chain (see fold_radiance)
+    float4* radiance;  // [cap] finished path radiance
+    uint32_t* q_extend[2];             // ping-pong extend queues
+    uint32_t* q_mat[MAT_NUM_QUEUES];   // per-material shade queues
+    uint32_t* counters;                // [FW_MAX_DEPTH + 2][FW_COUNTERS_PER_BOUNCE]
+    uint32_t cap;
+};
+
+struct Batch {
+    uint32_t pix0, npix, s0, ns;
+    uint32_t width, height;
+};
+
+FW_DEV void batch_path(const Batch& b, uint32_t p, uint32_t& pixel, uint32_t& sample) {
+    pixel = b.pix0 + p % b.npix;
+    sample = b.s0 + p / b.npix;
+}
+
+// render.rs:173-180 + camera.rs:109-116 + util.rs:31-33
+FW_DEV void primary_ray(const CameraRec& cam, uint32_t width, uint32_t height, uint32_t pixel, uint32_t sample,
+                        uint2 seed, float3& o, float3& d) {
+    uint32_t px = pixel % width;
+    uint32_t py = height - pixel / width;  // Coord::from_index: y counts down from `height`
+    RngKey key{seed, pixel, sample, 0u};
+    PhiloxStream rng(key, STREAM_CAMERA);
+    float u = ((float)px + rng.next()) / (float)width;
+    float v = ((float)py + rng.next()) / (float)height;
+    float3 rd = cam.lens_radius * random_in_unit_disk(rng);
+    float3 cu = f3(cam.u[0], cam.u[1], cam.u[2]), cv = f3(cam.v[0], cam.v[1], cam.v[2]);
+    float3 pos = f3(cam.position[0], cam.position[1], cam.position[2]);
+    float3 ll = f3(cam.lower_left[0], cam.lower_left[1], cam.lower_left[2]);
+    float3 hor = f3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
+    float3 ver = f3(cam.vertical[0], cam.vertical[1], cam.vertical[2]);
+    float3 offset = cu * rd.x + cv * rd.y;
+    o = pos + offset;
+    d = ll + u * hor + v * ver - pos - offset;
+}
+
+__global__ void __launch_bounds__(256) raygen_kernel(CameraRec cam, Batch b, uint2 seed, PathState ps) {
+    uint32_t total = b.npix * b.ns;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        uint32_t pixel, sample;
+        batch_path(b, p, pixel, sample);
+        float3 o, d;
+        primary_ray(cam, b.width, b.height, pixel, sample, seed, o, d);
+        ps.ray_o[p] = make_float4(o.x, o.y, o.z, 0.0f);
+        ps.ray_d[p] = make_float4(d.x, d.y, d.z, 0.0f);
+        ps.radiance[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+// Append `path` to queue `k` for every lane whose `mine` == k: one atomicAdd per warp per non-empty queue.
+template <int NQ>
+FW_DEV void warp_enqueue(uint32_t* const* queues, uint32_t* counters, int mine, uint32_t path) {
+    unsigned lane = threadIdx.x & 31u;
+    unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        unsigned mask = __ballot_sync(0xffffffffu, mine == k);
+        if (mask == 0u) continue;
+        int leader = __ffs(mask) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&counters[k], (uint32_t)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (mine == k) queues[k][base + __popc(mask & lt)] = path;
+    }
+}
+
+// extend: closest hit for every queued path; writes the hit record and sorts the path into its
+// material's shade queue (or the miss queue).
+template <bool USE_BVH>
+__global__ void __launch_bounds__(128) extend_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                     const uint32_t* __restrict__ q_in,
+                                                     const uint32_t* __restrict__ count_in, uint32_t n_direct,
+                                                     uint32_t* counters_out) {
+    uint32_t total = count_in ? *count_in : n_direct;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        uint32_t i = base + threadIdx.x;
+        int mine = -1;
+        uint32_t path = 0;
+        if (i < total) {
+            path = q_in ? q_in[i] : i;
+            float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
+            uint32_t pixel, sample;
+            batch_path(b, path, pixel, sample);
+            RngKey key{seed, pixel, sample, bounce};
+            HitRecord rec;
+            if (scene_closest_hit<USE_BVH, false>(S, f3(ro), f3(rd), key, rec, nullptr)) {
+                ps.hit_p[path] = make_float4(rec.point.x, rec.point.y, rec.point.z, rec.t);
+                ps.hit_n[path] = make_float4(rec.normal.x, rec.normal.y, rec.normal.z, __int_as_float(rec.material));
+                ps.hit_uv[path] = rec.uv;
+                mine = __ldg(&S.mats[rec.material].kind);
+            } else {
+                mine = MAT_MISS;
+            }
+        }
+        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
+    }
+}
+
+// render.rs:23 evaluated without recursion: colour = a0 * (a1 * (... (a_{k-1} * terminal))) with the same
+// right-nested association as `emit + attenuation * color(...)`; emit is zero at every scattering vertex
+// (material.rs:13-15), so the chain of attenuations is all that is needed.
+FW_DEV float3 fold_radiance(const PathState& ps, uint32_t path, uint32_t bounce, float3 terminal) {
+    float3 x = terminal;
+    for (int k = (int)bounce - 1; k >= 0; --k) {
+        float4 a = ps.atten[(size_t)k * ps.cap + path];
+        x = f3(a.x, a.y, a.z) * x;
+    }
+    return x;
+}
+
+// render.rs:31 — environment lookup for rays that left the scene
+__global__ void __launch_bounds__(256) miss_kernel(DeviceScene S, PathState ps, uint32_t bounce,
+                                                   const uint32_t* __restrict__ counters) {
+    uint32_t total = counters[MAT_MISS];
+    const uint32_t* q = ps.q_mat[MAT_MISS];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t path = q[i];
+        float3 env = environment_sample(S.env, f3(ps.ray_d[path]));
+        float3 c = fold_radiance(ps, path, bounce, env);
+        ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
+    }
+}
+
+// render.rs:20,25-28 with material.rs:174-180 — emissive surfaces end the path with their texture value
+__global__ void __launch_bounds__(256) shade_emissive_kernel(DeviceScene S, PathState ps, uint32_t bounce,
+                                                             const uint32_t* __restrict__ counters) {
+    uint32_t total = counters[MAT_EMISSIVE];
+    const uint32_t* q = ps.q_mat[MAT_EMISSIVE];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t path = q[i];
+        float4 hp = ps.hit_p[path], hn = ps.hit_n[path];
+        int tex = __ldg(&S.mats[__float_as_int(hn.w)].tex);
+        float3 emit = texture_sample(S, tex, ps.hit_uv[path], f3(hp));
+        float3 c = fold_radiance(ps, path, bounce, emit);
+        ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
+    }
+}
+
+// Scattering materials: write the next ray + this vertex's attenuation, re-queue the path for extend.
+// Not launched for bounce == FW_MAX_DEPTH (render.rs:21: no scatter at depth 10; emit is zero).
+template <int MAT>
+__global__ void __launch_bounds__(256) shade_scatter_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
+                                                            uint32_t bounce, const uint32_t* __restrict__ counters_in,
+                                                            uint32_t* q_out, uint32_t* counters_out) {
+    uint32_t total = counters_in[MAT];
+    const uint32_t* q = ps.q_mat[MAT];
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        uint32_t i = base + threadIdx.x;
+        int mine = -1;
+        uint32_t path = 0;
+        if (i < total) {
+            path = q[i];
+            float4 hp = ps.hit_p[path], hn = ps.hit_n[path];
+            float3 point = f3(hp), normal = f3(hn);
+            const float4* mq = reinterpret_cast<const float4*>(&S.mats[__float_as_int(hn.w)]);
+            float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);  // (kind, tex, param, -), (albedo, -)
+            uint32_t pixel, sample;
+            batch_path(b, path, pixel, sample);
+            RngKey key{seed, pixel, sample, bounce};
+            PhiloxStream rng(key, STREAM_SCATTER);
+            ScatterOut out;
+            if (MAT == MAT_LAMBERTIAN) {
+                scatter_lambertian(S, __float_as_int(m0.y), point, normal, ps.hit_uv[path], rng, out);
+            } else if (MAT == MAT_METAL) {
+                scatter_metal(f3(m1), m0.z, f3(ps.ray_d[path]), point, normal, rng, out);
+            } else if (MAT == MAT_DIELECTRIC) {
+                scatter_dielectric(m0.z, f3(ps.ray_d[path]), point, normal, rng, out);
+            } else {
+                scatter_isotropic(S, __float_as_int(m0.y), point, ps.hit_uv[path], rng, out);
+            }
+            if (out.scattered) {
+                ps.ray_o[path] = make_float4(out.origin.x, out.origin.y, out.origin.z, 0.0f);
+                ps.ray_d[path] = make_float4(out.dir.x, out.dir.y, out.dir.z, 0.0f);
+                ps.atten[(size_t)bounce * ps.cap + path] =
+                    make_float4(out.attenuation.x, out.attenuation.y, out.attenuation.z, 0.0f);
+                mine = 0;
+            }
+            // absorbed (metal below the surface): radiance stays 0 (render.rs:25)
+        }
+        warp_enqueue<1>(&q_out, counters_out + 6, mine, path);
+    }
+}
+
+// render.rs:177-182 `total_color += color(...)`: samples of a pixel are added in sample order, so the fp32
+// sum is independent of queue order and identical for any batch split along the sample axis.
+__global__ void __launch_bounds__(256) accumulate_kernel(float* __restrict__ sum, PathState ps, Batch b) {
+    for (uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x; pl < b.npix; pl += gridDim.x * blockDim.x) {
+        size_t pix = (size_t)b.pix0 + pl;
+        float r = sum[3 * pix], g = sum[3 * pix + 1], bl = sum[3 * pix + 2];
+        for (uint32_t s = 0; s < b.ns; ++s) {
+            float4 c = ps.radiance[(size_t)s * b.npix + pl];
+            r += c.x; g += c.y; bl += c.z;
+        }
+        sum[3 * pix] = r; sum[3 * pix + 1] = g; sum[3 * pix + 2] = bl;
+    }
+}
+
+// render.rs:184-189 + util.rs:14-23: mean, powf(1/gamma), clamp, *255.99 -> saturating u8 (NaN -> 0)
+FW_DEV unsigned char quantise(float mean, float inv_gamma) {
+    float x = powf(mean, inv_gamma);
+    if (x < 0.0f) x = 0.0f;
+    if (x > 1.0f) x = 1.0f;
+    float y = x * 255.99f;
+    if (!(y == y)) return 0;
+    return (unsigned char)fminf(fmaxf(truncf(y), 0.0f), 255.0f);
+}
+__global__ void __launch_bounds__(256) resolve_kernel(const float* __restrict__ sum, uint32_t npix, float samples,
+                                                      float gamma, unsigned char* __restrict__ rgb) {
+    float inv_gamma = 1.0f / gamma;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        rgb[3 * i] = quantise(sum[3 * i] / samples, inv_gamma);
+        rgb[3 * i + 1] = quantise(sum[3 * i + 1] / samples, inv_gamma);
+        rgb[3 * i + 2] = quantise(sum[3 * i + 2] / samples, inv_gamma);
+    }
+}
+
+// ---- probe kernels (the parity gates of BASELINE.json) -------------------------------------------------
+
+__global__ void primary_rays_probe(CameraRec cam, uint32_t width, uint32_t height, uint32_t sample, uint2 seed,
+                                   uint32_t pix_begin, uint32_t n, float* origins, float* dirs) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float3 o, d;
+        primary_ray(cam, width, height, pix_begin + i, sample, seed, o, d);
+        origins[3 * i] = o.x; origins[3 * i + 1] = o.y; origins[3 * i + 2] = o.z;
+        dirs[3 * i] = d.x; dirs[3 * i + 1] = d.y; dirs[3 * i + 2] = d.z;
+    }
+}
+
+struct FirstHitOut {
+    int *obj, *prim, *material;
+    float *t, *point, *normal, *uv;
+    unsigned long long* counters;  // [2] node tests, prim tests
+};
+template <bool USE_BVH>
+__global__ void first_hit_probe(DeviceScene S, uint2 seed, uint32_t n, const float* origins, const float* dirs,
+                                const uint32_t* pixel, const uint32_t* sample, const uint32_t* bounce,
+                                FirstHitOut out) {
+    Counters cnt{0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float3 o = f3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        float3 d = f3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        RngKey key{seed, pixel ? pixel[i] : i, sample ? sample[i] : 0u, bounce ? bounce[i] : 0u};
+        HitRecord rec;
+        if (scene_closest_hit<USE_BVH, true>(S, o, d, key, rec, &cnt)) {
+            out.obj[i] = rec.obj; out.prim[i] = rec.prim; out.material[i] = rec.material; out.t[i] = rec.t;
+            out.point[3 * i] = rec.point.x; out.point[3 * i + 1] = rec.point.y; out.point[3 * i + 2] = rec.point.z;
+            out.normal[3 * i] = rec.normal.x; out.normal[3 * i + 1] = rec.normal.y; out.normal[3 * i + 2] = rec.normal.z;
+            out.uv[2 * i] = rec.uv.x; out.uv[2 * i + 1] = rec.uv.y;
+        } else {
+            out.obj[i] = -1; out.prim[i] = 0; out.material[i] = -1; out.t[i] = 0.0f;
+            out.point[3 * i] = out.point[3 * i + 1] = out.point[3 * i + 2] = 0.0f;
+            out.normal[3 * i] = out.normal[3 * i + 1] = out.normal[3 * i + 2] = 0.0f;
+            out.uv[2 * i] = out.uv[2 * i + 1] = 0.0f;
+        }
+    }
+    atomicAdd(&out.counters[0], cnt.node_tests);
+    atomicAdd(&out.counters[1], cnt.prim_tests);
+}
+
+struct ScatterProbeIO {
+    const int* material;
+    const float *ray_o, *ray_d, *hit_t, *hit_point, *hit_normal, *hit_uv, *uniforms;
+    uint32_t nu;
+    float* emit;
+    int* scattered;
+    float *atten, *out_o, *out_d;
+    int* consumed;
+};
+__global__ void scatter_step_probe(DeviceScene S, uint32_t n, ScatterProbeIO io) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int mat = io.material[i];
+        const float4* mq = reinterpret_cast<const float4*>(&S.mats[mat]);
+        float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);
+        int kind = __float_as_int(m0.x), tex = __float_as_int(m0.y);
+        float3 in_d = f3(io.ray_d[3 * i], io.ray_d[3 * i + 1], io.ray_d[3 * i + 2]);
+        float3 point = f3(io.hit_point[3 * i], io.hit_point[3 * i + 1], io.hit_point[3 * i + 2]);
+        float3 normal = f3(io.hit_normal[3 * i], io.hit_normal[3 * i + 1], io.hit_normal[3 * i + 2]);
+        float2 uv = make_float2(io.hit_uv[2 * i], io.hit_uv[2 * i + 1]);
+        ArrayStream rng(io.uniforms + (size_t)i * io.nu, (int)io.nu);
+        ScatterOut out;
+        out.scattered = false;
+        out.attenuation = out.origin = out.dir = f3(0.0f, 0.0f, 0.0f);
+        float3 emit = f3(0.0f, 0.0f, 0.0f);
+        switch (kind) {
+            case MAT_LAMBERTIAN: scatter_lambertian(S, tex, point, normal, uv, rng, out); break;
+            case MAT_METAL: scatter_metal(f3(m1), m0.z, in_d, point, normal, rng, out); break;
+            case MAT_DIELECTRIC: scatter_dielectric(m0.z, in_d, point, normal, rng, out); break;
+            case MAT_EMISSIVE: emit = texture_sample(S, tex, uv, point); break;
+            case MAT_ISOTROPIC: scatter_isotropic(S, tex, point, uv, rng, out); break;
+        }
+        if (!out.scattered) out.attenuation = out.origin = out.dir = f3(0.0f, 0.0f, 0.0f);
+        io.emit[3 * i] = emit.x; io.emit[3 * i + 1] = emit.y; io.emit[3 * i + 2] = emit.z;
+        io.scattered[i] = out.scattered ? 1 : 0;
+        io.atten[3 * i] = out.attenuation.x; io.atten[3 * i + 1] = out.attenuation.y; io.atten[3 * i + 2] = out.attenuation.z;
+        io.out_o[3 * i] = out.origin.x; io.out_o[3 * i + 1] = out.origin.y; io.out_o[3 * i + 2] = out.origin.z;
+        io.out_d[3 * i] = out.dir.x; io.out_d[3 * i + 1] = out.dir.y; io.out_d[3 * i + 2] = out.dir.z;
+        io.consumed[i] = rng.overrun ? -1 : rng.i;
+    }
+}
+
+__global__ void env_sample_probe(DeviceScene S, uint32_t n, const float* dirs, float* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float3 c = environment_sample(S.env, f3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+        out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+    }
+}
+__global__ void texture_sample_probe(DeviceScene S, int tex, uint32_t n, const float* uv, const float* point, float* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float3 c = texture_sample(S, tex, make_float2(uv[2 * i], uv[2 * i + 1]),
+                                  f3(point[3 * i], point[3 * i + 1], point[3 * i + 2]));
+        out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+    }
+}
+
+}  // namespace fw

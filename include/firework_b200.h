@@ -1,0 +1,144 @@
+/* firework_b200.h — C ABI of the B200-native replacement for firework's rendering hot path.
+ *
+ * The reference (ritobanrc/firework, Rust) has no FFI layer; the seam this library sits behind is the call
+ *
+ *     Renderer::render(&self, scene: Scene) -> Vec<Color>            (reference src/render.rs:109)
+ *
+ * reached from src/main.rs:42 and every examples/*.rs.  `Scene` holds only trait objects
+ * (src/scene.rs:20-24), so the type-erased form any host can hand over is the serde document
+ * `serde_yaml::to_string(&scene)` (src/scene.rs:18, src/serde_compat.rs) — that text is what
+ * fw_scene_from_yaml takes.  INTEGRATION.md shows the Rust binding (`extern "C"` + build.rs) a
+ * maintainer would add to call this from `Renderer::render`.
+ *
+ * Conventions: plain pointers and sizes; the caller owns every buffer it passes; the library owns
+ * fw_scene until fw_scene_destroy; every call returns 0 on success or a negative fw_status, and
+ * fw_last_error() (thread-local) describes the failure; nothing throws or aborts across the boundary.
+ * Calls on one fw_scene must not overlap; different scenes may be used from different threads.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with FW_ERR_CUDA.
+ */
+#ifndef FIREWORK_B200_H
+#define FIREWORK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fw_scene fw_scene;
+
+typedef enum fw_status {
+    FW_OK = 0,
+    FW_ERR_PARSE = -1,    /* malformed YAML or unknown type tag                      */
+    FW_ERR_SCENE = -2,    /* semantically invalid scene (no objects, bad indices...) */
+    FW_ERR_ASSET = -3,    /* an ImageTexture / HdrEnvironment asset was not provided */
+    FW_ERR_CUDA = -4,     /* CUDA runtime failure (incl. no device)                  */
+    FW_ERR_ARG = -5,      /* bad argument                                            */
+    FW_ERR_STATE = -6     /* call order violated (e.g. render before commit)         */
+} fw_status;
+
+/* Renderer + CameraSettings of the reference (src/render.rs:57-77, src/camera.rs:18-24), as one POD.
+ * `samples` is the spp the image is normalised by (render.rs:184); the call renders the sample indices
+ * [sample_begin, sample_begin + sample_count), which is how the sample range is sharded across GPUs.
+ * `seed` keys the counter-based RNG that replaces tiny_rng::LcRng::new(idx) (render.rs:172). */
+typedef struct fw_params {
+    uint32_t width, height;
+    uint32_t samples;
+    uint32_t sample_begin, sample_count;
+    uint32_t use_bvh;                  /* Renderer::use_bvh (render.rs:117-121, 128-132) */
+    float gamma;                       /* Renderer::gamma   (render.rs:185-187)          */
+    float cam_pos[3], look_at[3];
+    float vfov, aperture, focus_dist;  /* camera.rs:74-107                                */
+    uint64_t seed;
+} fw_params;
+
+typedef struct fw_stats {
+    uint64_t samples;        /* width*height*sample_count                                   */
+    uint64_t rays;           /* top-level closest-hit queries (calls of color(), render.rs:19) */
+    uint64_t launches;       /* kernels launched by this call                               */
+    double ms_device;        /* CUDA-event time of the device work of this call              */
+    double ms_extend;        /* CUDA-event time spent in the extend kernels (0 unless profiling enabled) */
+    uint64_t extend_launches;
+} fw_stats;
+
+/* ---- scene lifecycle ----------------------------------------------------------------------------------
+ * replaces: serde_yaml::from_reader::<Scene> (src/main.rs:25-26) + SceneInternal::from(scene)
+ *           (src/render.rs:113, src/scene.rs:111-135, 279-292) + build_bvh (src/bvh.rs:79-113).      */
+int fw_scene_from_yaml(const char* text, size_t len, fw_scene** out);
+int fw_scene_from_file(const char* path, fw_scene** out);
+void fw_scene_destroy(fw_scene* scene);
+
+/* Assets named by the document (ImageTexture `value:` — src/texture.rs:251-278; HdrEnvironment —
+ * examples/hdri_test.rs:22-67).  The host decodes them and hands over texels. kind: 0 = image, 1 = HDR. */
+int fw_scene_num_assets(const fw_scene* scene);
+const char* fw_scene_asset_path(const fw_scene* scene, int index);
+int fw_scene_asset_kind(const fw_scene* scene, int index);
+int fw_scene_set_image(fw_scene* scene, int index, uint32_t width, uint32_t height, const uint8_t* rgba8);
+int fw_scene_set_hdr(fw_scene* scene, int index, uint32_t width, uint32_t height, const float* rgb32f);
+
+/* fw_scene_build_host: builds the BVHs with the reference's split rule (src/bvh.rs:21-71) and flattens the
+ * scene into pointer-free arrays — host only, no CUDA.  fw_scene_commit: the same, then uploads to `device`. */
+int fw_scene_build_host(fw_scene* scene);
+int fw_scene_commit(fw_scene* scene, int device);
+
+/* Introspection (host data; valid after fw_scene_build_host or fw_scene_commit). */
+int fw_scene_num_objects(const fw_scene* scene);
+int fw_scene_num_nodes(const fw_scene* scene);
+int fw_scene_top_leaf_order(const fw_scene* scene, int* out, int capacity);          /* object ids, DFS leaf order */
+int fw_scene_object_aabb(const fw_scene* scene, int object, float out_min_max[6]);   /* scene.rs:167-212 */
+int fw_scene_mesh_leaf_order(const fw_scene* scene, int object, int* out, int capacity); /* triangle ids */
+
+/* ---- the hot path -------------------------------------------------------------------------------------
+ * replaces: the per-pixel loop of Renderer::render (src/render.rs:123-196).
+ * rgb_out : width*height*3 u8, row 0 = top of image (== Vec<Color>); may be NULL.
+ * sum_out : width*height*3 fp32 un-normalised radiance sums of the rendered sample range; may be NULL.
+ * Host buffers; the call is synchronous.                                                                */
+int fw_render(fw_scene* scene, const fw_params* params, uint8_t* rgb_out, float* sum_out, fw_stats* stats);
+
+/* Device-resident variant for multi-GPU sharding: ADDS the sample range into d_sum (device pointer,
+ * width*height*3 fp32, on the scene's device) on `cuda_stream` (a cudaStream_t, or NULL for the scene's own
+ * stream) and returns once the work is enqueued and statistics are read back. */
+int fw_render_accumulate_device(fw_scene* scene, const fw_params* params, float* d_sum, void* cuda_stream,
+                                fw_stats* stats);
+/* render.rs:184-189 + util.rs:14-23 on a device sum buffer: d_rgb = quantise((d_sum / samples)^(1/gamma)). */
+int fw_resolve_device(fw_scene* scene, const float* d_sum, uint32_t npix, uint32_t samples, float gamma,
+                      uint8_t* d_rgb, void* cuda_stream);
+
+/* ---- probe entry points for the parity gates (host buffers) -----------------------------------------------
+ * fw_primary_rays : camera.rs:109-116 + render.rs:173-180 for sample index `sample`, pixels [pix_begin, +n).
+ * fw_first_hit    : render.rs:19 `root.hit(r, 0.001, 2e9, rng)`; obj = -1 on miss. pixel/sample/bounce key
+ *                   the ConstantMedium draw (may be NULL: pixel = i, sample = bounce = 0).
+ *                   counters (nullable) receives {node tests, primitive tests}.
+ * fw_scatter_step : render.rs:20-22 emit + scatter with EXPLICIT uniforms (nu per item, consumed in order).
+ * fw_env_sample / fw_texture_sample : render.rs:31 / texture.rs lookups.                                 */
+int fw_primary_rays(fw_scene* scene, const fw_params* params, uint32_t sample, uint32_t pix_begin, uint32_t n,
+                    float* origins, float* dirs);
+int fw_first_hit(fw_scene* scene, int use_bvh, uint64_t seed, uint32_t n, const float* origins, const float* dirs,
+                 const uint32_t* pixel, const uint32_t* sample, const uint32_t* bounce, int32_t* obj, int32_t* prim,
+                 int32_t* material, float* t, float* point, float* normal, float* uv, uint64_t counters[2]);
+int fw_scatter_step(fw_scene* scene, uint32_t n, const int32_t* material, const float* ray_o, const float* ray_d,
+                    const float* hit_t, const float* hit_point, const float* hit_normal, const float* hit_uv,
+                    const float* uniforms, uint32_t nu, float* emit, int32_t* scattered, float* atten, float* out_o,
+                    float* out_d, int32_t* consumed);
+int fw_env_sample(fw_scene* scene, uint32_t n, const float* dirs, float* out);
+int fw_texture_sample(fw_scene* scene, int texture, uint32_t n, const float* uv, const float* point, float* out);
+int fw_material_texture(const fw_scene* scene, int material);  /* texture index of a material, or -1 */
+int fw_camera(const fw_params* params, float out24[24]);        /* camera.rs:74-107 constants, host only */
+
+/* ---- misc ----------------------------------------------------------------------------------------------- */
+const char* fw_last_error(void);
+const char* fw_version(void);
+int fw_device_count(void);
+/* Microbenchmarks used by bench.py for the roofline denominators: dependent-free FP32 FMA rate (TFLOP/s) and
+ * L2-resident streaming read bandwidth (GB/s) on `device`. */
+int fw_measure_peaks(int device, double* fp32_tflops, double* l2_gbs, int* sm_count, int* sm_clock_khz);
+/* Per-kernel CUDA-event profiling of extend launches (adds synchronisation; off by default). */
+int fw_set_profiling(fw_scene* scene, int enabled);
+/* Maximum number of paths in flight per batch (0 = default). */
+int fw_set_batch_paths(fw_scene* scene, uint64_t paths);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIREWORK_B200_H */
