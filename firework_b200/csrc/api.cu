@@ -35,6 +35,7 @@ static_assert(sizeof(ShapeRec) == 48 && sizeof(MeshRec) == 32 && sizeof(MatRec) 
 struct fw_scene {
     SceneDesc desc;
     HostFlat flat;
+    uint64_t h2d_bytes = 0;  // bytes copied host->device by commit
     bool built = false;      // host-side BVH build + flattening done
     bool committed = false;  // uploaded to the device
     int device = 0;
@@ -66,6 +67,7 @@ static int upload(fw_scene* sc, const std::vector<T>& host, const T** dev) {
     sc->allocs.push_back(p);
     FW_CUDA(cudaMemset(p, 0, bytes));
     if (!host.empty()) FW_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    sc->h2d_bytes += host.size() * sizeof(T);
     *dev = reinterpret_cast<const T*>(p);
     return FW_OK;
 }
@@ -190,6 +192,7 @@ static int make_texture(fw_scene* sc, const void* src, uint32_t w, uint32_t h, b
     sc->arrays.push_back(arr);
     size_t row = (size_t)w * (is_float ? 16 : 4);
     FW_CUDA(cudaMemcpy2DToArray(arr, 0, 0, src, row, row, h, cudaMemcpyHostToDevice));
+    sc->h2d_bytes += row * h;
     cudaResourceDesc rd;
     memset(&rd, 0, sizeof(rd));
     rd.resType = cudaResourceTypeArray;
@@ -273,6 +276,7 @@ int fw_scene_commit(fw_scene* sc, int device) {
     return FW_OK;
 }
 
+uint64_t fw_scene_device_bytes(const fw_scene* sc) { return sc ? sc->h2d_bytes : 0; }
 int fw_scene_num_objects(const fw_scene* sc) { return sc ? (int)sc->desc.objects.size() : 0; }
 int fw_scene_num_nodes(const fw_scene* sc) { return sc && sc->built ? (int)(sc->flat.nodes.size() / 2) : 0; }
 int fw_scene_top_leaf_order(const fw_scene* sc, int* out, int cap) {

@@ -71,7 +71,8 @@ struct EnvRec {
     cudaTextureObject_t tex;  // HdrEnvironment: float4 point-sampled
 };
 
-// BVH node = 2 x float4:  lo = (min.xyz, asfloat(code)),  hi = (max.xyz, asfloat(count))
+// BVH node = 2 x float4:  lo = (min.xyz, asfloat(code)),  hi = (max.xyz, asfloat(flags))
+//   flags bit 0 : some item below has a box that does not bound its geometry (Disk) -> never distance-cull
 //   code >= 0 : interior, children at nodes code and code+1 (siblings adjacent, 64-byte aligned pair)
 //   code <  0 : leaf; p = ~code, items [p >> 1, (p >> 1) + (p & 1) + 1) of the tree's item list
 //               (1 or 2 items: bvh.rs Leaf / DoubleLeaf)

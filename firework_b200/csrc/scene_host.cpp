@@ -388,6 +388,7 @@ struct BuildNode {
     int left = -1, right = -1;  // interior
     int first = -1, count = 0;  // leaf: range in the ordered item list
     int depth = 0;
+    bool unbounded = false;     // some item below has a box that does not bound its geometry
 };
 struct Builder {
     const std::vector<Box>& boxes;
@@ -395,6 +396,7 @@ struct Builder {
     std::vector<int> order;
     std::vector<BuildNode> nodes;
     bool nan = false;
+    const std::vector<uint8_t>* unbounded = nullptr;
     explicit Builder(const std::vector<Box>& b) : boxes(b) {
         centers.reserve(b.size());
         for (const Box& x : b) centers.push_back(box_center(x));
@@ -414,10 +416,12 @@ struct Builder {
             nodes[id].box = boxes[order[lo]];
             nodes[id].first = lo;
             nodes[id].count = 1;
+            nodes[id].unbounded = unbounded && (*unbounded)[order[lo]];
         } else if (n == 2) {
             nodes[id].box = box_expand(boxes[order[lo]], boxes[order[lo + 1]]);
             nodes[id].first = lo;
             nodes[id].count = 2;
+            nodes[id].unbounded = unbounded && ((*unbounded)[order[lo]] || (*unbounded)[order[lo + 1]]);
         } else {
             int half = n / 2;
             int l = build(lo, half, depth + 1);
@@ -425,6 +429,7 @@ struct Builder {
             nodes[id].left = l;
             nodes[id].right = r;
             nodes[id].box = box_expand(nodes[l].box, nodes[r].box);
+            nodes[id].unbounded = nodes[l].unbounded || nodes[r].unbounded;
         }
         return id;
     }
@@ -436,13 +441,15 @@ static inline float as_float(int i) {
 }
 }  // namespace
 
-bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& err) {
+bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& err,
+               const std::vector<uint8_t>* item_unbounded) {
     out = FlatBVH();
     if (item_boxes.empty()) {
         err = "cannot build a BVH over zero items (the reference recurses forever: bvh.rs:59)";
         return false;
     }
     Builder b(item_boxes);
+    b.unbounded = item_unbounded;
     b.nodes.reserve(item_boxes.size() * 2);
     int root = b.build(0, (int)item_boxes.size(), 0);
     if (b.nan) {
@@ -463,10 +470,10 @@ bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& er
         int a, bb;
         if (n.count > 0) {
             a = ~(n.first * 2 + (n.count - 1));  // leaf code: items [first, first + count), count in {1, 2}
-            bb = n.count;
+            bb = n.unbounded ? 1 : 0;
         } else {
             a = next;
-            bb = 0;
+            bb = n.unbounded ? 1 : 0;
             next += 2;
             if ((int)out.nodes.size() < 2 * next) out.nodes.resize(2 * (size_t)next, float4{0, 0, 0, 0});
             q.emplace_back(n.left, a);
@@ -620,6 +627,27 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         return false;
     };
 
+    // Does the shape's bounding box really bound its geometry?  Disk's does not (disk.rs:85-90 is degenerate in
+    // x and z); a deserialised Rect3d may list faces outside pos..pos+size.
+    std::function<bool(int)> shape_unbounded = [&](int si) -> bool {
+        const ShapeRec& s = desc.shapes[si];
+        if (s.kind == SH_DISK) return true;
+        if (s.kind == SH_MEDIUM) return shape_unbounded(s.i0);
+        if (s.kind == SH_RECT3D) {
+            Box b;
+            shape_box(si, b);
+            for (int f = 0; f < s.i1; ++f) {
+                Box fb;
+                shape_box(s.i0 + f, fb);
+                if (fb.mn.x < b.mn.x - 0.011f || fb.mn.y < b.mn.y - 0.011f || fb.mn.z < b.mn.z - 0.011f ||
+                    fb.mx.x > b.mx.x + 0.011f || fb.mx.y > b.mx.y + 0.011f || fb.mx.z > b.mx.z + 0.011f)
+                    return true;
+            }
+        }
+        return false;
+    };
+    std::vector<uint8_t> obj_unbounded(desc.objects.size(), 0);
+
     size_t nobj = desc.objects.size();
     out.obj_aabb.resize(nobj);
     for (size_t i = 0; i < nobj; ++i) {
@@ -658,11 +686,12 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
             out.obj_irot.push_back(float4{Ri.c[c].x, Ri.c[c].y, Ri.c[c].z, 0});
         }
         if (s.kind == SH_MEDIUM) out.has_medium = true;
+        obj_unbounded[i] = shape_unbounded(o.shape) ? 1 : 0;
     }
 
     // top-level BVH (bvh.rs:79-98), always built: linear-scan renders simply do not use it
     FlatBVH top;
-    if (!build_bvh(out.obj_aabb, top, err)) return false;
+    if (!build_bvh(out.obj_aabb, top, err, &obj_unbounded)) return false;
     out.top_items = top.items;
     out.top_depth = top.max_depth;
     out.top_nodes = (int)(top.nodes.size() / 2);

@@ -63,7 +63,10 @@ struct FlatBVH {
     int max_depth = 0;
 };
 // The reference's median split (bvh.rs:21-71): stable sort on centroid[depth % 3], leaves of 1 or 2.
-bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& err);
+// `item_unbounded` (optional, same length as item_boxes) marks items whose box does NOT bound their geometry
+// (Disk: disk.rs:85-90); every node above such an item is flagged so the traversal never distance-culls it.
+bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& err,
+               const std::vector<uint8_t>* item_unbounded = nullptr);
 
 struct HostFlat {
     std::vector<float4> nodes;

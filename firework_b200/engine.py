@@ -69,6 +69,9 @@ class NativeScene:
     def num_nodes(self):
         return N.lib().fw_scene_num_nodes(self._h)
 
+    def device_bytes(self):
+        return int(N.lib().fw_scene_device_bytes(self._h))
+
     def top_leaf_order(self):
         n = self.num_objects()
         out = np.zeros(n, np.int32)

@@ -88,6 +88,7 @@ int fw_scene_num_nodes(const fw_scene* scene);
 int fw_scene_top_leaf_order(const fw_scene* scene, int* out, int capacity);          /* object ids, DFS leaf order */
 int fw_scene_object_aabb(const fw_scene* scene, int object, float out_min_max[6]);   /* scene.rs:167-212 */
 int fw_scene_mesh_leaf_order(const fw_scene* scene, int object, int* out, int capacity); /* triangle ids */
+uint64_t fw_scene_device_bytes(const fw_scene* scene);  /* host->device bytes copied by fw_scene_commit */
 
 /* ---- the hot path -------------------------------------------------------------------------------------
  * replaces: the per-pixel loop of Renderer::render (src/render.rs:123-196).

@@ -193,6 +193,8 @@ struct Rng {
 // ------------------------------------------------------------------------------------------------
 struct Counters {
     uint64_t rays = 0, aabb_tests = 0, prim_tests = 0;
+    // per-kind breakdown of prim_tests + object transforms, for the roofline's algorithmic flop / byte counts
+    uint64_t sphere = 0, rect = 0, tri = 0, conic = 0, xform_rot = 0, xform_trans = 0;
 };
 static thread_local Counters g_cnt;
 
@@ -289,6 +291,7 @@ struct Sphere : Hitable {
     int material;
     bool hit(const Ray& r, float t_min, float t_max, Rng&, RaycastHit& out) const override {
         ++g_cnt.prim_tests;
+        ++g_cnt.sphere;
         Vec3 o = r.origin, d = r.dir;
         float a = dot(d, d);
         float b = 2.0f * dot(o, d);
@@ -327,6 +330,7 @@ struct AARect : Hitable {
     int material;
     bool hit(const Ray& r, float t_min, float t_max, Rng&, RaycastHit& out) const override {
         ++g_cnt.prim_tests;
+        ++g_cnt.rect;
         float t = (k - r.origin[ak]) / r.dir[ak];
         if (t < t_min || t > t_max) return false;
         Vec3 point = r.point(t);
@@ -375,6 +379,7 @@ struct Disk : Hitable {
     int material;
     bool hit(const Ray& r, float t_min, float t_max, Rng&, RaycastHit& out) const override {
         ++g_cnt.prim_tests;
+        ++g_cnt.conic;
         if (r.dir.y == 0.0f) return false;
         float t = -r.origin.y / r.dir.y;
         if (t < t_min || t > t_max) return false;
@@ -422,6 +427,7 @@ struct Cylinder : Hitable {
     }
     bool hit(const Ray& r, float t_min, float t_max, Rng&, RaycastHit& out) const override {
         ++g_cnt.prim_tests;
+        ++g_cnt.conic;
         Vec3 o = r.origin, d = r.dir;
         float a = d.x * d.x + d.z * d.z;
         float b = 2.0f * (d.x * o.x + d.z * o.z);
@@ -465,6 +471,7 @@ struct Cone : Hitable {
     }
     bool hit(const Ray& r, float t_min, float t_max, Rng&, RaycastHit& out) const override {
         ++g_cnt.prim_tests;
+        ++g_cnt.conic;
         Vec3 o = r.origin, d = r.dir;
         float r2_div_h2 = radius * radius / (height * height);
         float a = d.x * d.x + d.z * d.z - r2_div_h2 * d.y * d.y;
@@ -509,6 +516,7 @@ struct Triangle {
     size_t index;
     bool hit(const Ray& r, float t_min, float t_max, Rng&, RaycastHit& out) const {
         ++g_cnt.prim_tests;
+        ++g_cnt.tri;
         const TriangleMesh& m = *mesh;
         size_t base = 3 * index;
         Vec3 p0 = m.verts[m.indicies[base]], p1 = m.verts[m.indicies[base + 1]],
@@ -756,8 +764,10 @@ struct RenderObjectInternal {
     bool hit(const Ray& r, float t_min, float t_max, Rng& rand, RaycastHit& out) const {
         Ray new_ray;
         if (cos_trace() < 0.999f) {
+            ++g_cnt.xform_rot;
             new_ray = Ray{inv_rotation_mat * (r.origin - position), inv_rotation_mat * r.dir};
         } else {
+            ++g_cnt.xform_trans;
             new_ray = Ray{r.origin - position, r.dir};
         }
         if (obj->hit(new_ray, t_min, t_max, rand, out)) {
@@ -1478,6 +1488,8 @@ struct OrcStats {
     uint64_t samples, rays, aabb_tests, prim_tests;
     double seconds;
     int threads;
+    int pad;
+    uint64_t sphere, rect, tri, conic, xform_rot, xform_trans;
 };
 
 // The camera (camera.rs:74-107) as 8 Vec3-ish constants: position, horizontal, vertical, lower_left, u, v, w,
@@ -1602,7 +1614,7 @@ int orc_render(void* sp, const RenderParams* p, uint32_t pix_begin, uint32_t pix
     Scene* s = (Scene*)sp;
     if (p->use_bvh && !s->bvh) return -2;
     Camera cam = make_camera(*p);
-    uint64_t rays = 0, aabb = 0, prim = 0;
+    uint64_t rays = 0, aabb = 0, prim = 0, k_sph = 0, k_rect = 0, k_tri = 0, k_con = 0, k_xr = 0, k_xt = 0;
     int threads = 1;
 #ifdef _OPENMP
     if (num_threads > 0) omp_set_num_threads(num_threads);
@@ -1613,7 +1625,7 @@ int orc_render(void* sp, const RenderParams* p, uint32_t pix_begin, uint32_t pix
 #endif
     if (pix_count == 0) pix_count = p->width * p->height - pix_begin;
     // render.rs:127 — one task per pixel (rayon work stealing ~ schedule(dynamic))
-#pragma omp parallel for schedule(dynamic, 16) reduction(+ : rays, aabb, prim)
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : rays, aabb, prim, k_sph, k_rect, k_tri, k_con, k_xr, k_xt)
     for (int64_t k = 0; k < (int64_t)pix_count; ++k) {
         size_t idx = pix_begin + (size_t)k;
         g_cnt = Counters();
@@ -1628,10 +1640,14 @@ int orc_render(void* sp, const RenderParams* p, uint32_t pix_begin, uint32_t pix
         if (sum_out) { sum_out[3 * idx] = total.x; sum_out[3 * idx + 1] = total.y; sum_out[3 * idx + 2] = total.z; }
         if (rgb_out) resolve_pixel(total, p->samples, p->gamma, rgb_out + 3 * idx);
         rays += g_cnt.rays; aabb += g_cnt.aabb_tests; prim += g_cnt.prim_tests;
+        k_sph += g_cnt.sphere; k_rect += g_cnt.rect; k_tri += g_cnt.tri; k_con += g_cnt.conic;
+        k_xr += g_cnt.xform_rot; k_xt += g_cnt.xform_trans;
     }
     if (stats) {
         stats->samples = (uint64_t)pix_count * p->sample_count;
         stats->rays = rays; stats->aabb_tests = aabb; stats->prim_tests = prim;
+        stats->sphere = k_sph; stats->rect = k_rect; stats->tri = k_tri; stats->conic = k_con;
+        stats->xform_rot = k_xr; stats->xform_trans = k_xt;
 #ifdef _OPENMP
         stats->seconds = omp_get_wtime() - t0;
 #else

@@ -28,7 +28,9 @@ class OrcParams(C.Structure):
 
 class OrcStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("aabb_tests", C.c_uint64),
-                ("prim_tests", C.c_uint64), ("seconds", C.c_double), ("threads", C.c_int)]
+                ("prim_tests", C.c_uint64), ("seconds", C.c_double), ("threads", C.c_int), ("pad", C.c_int),
+                ("sphere", C.c_uint64), ("rect", C.c_uint64), ("tri", C.c_uint64), ("conic", C.c_uint64),
+                ("xform_rot", C.c_uint64), ("xform_trans", C.c_uint64)]
 
 
 def build(force: bool = False) -> None:
