@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -32,6 +33,25 @@ static int set_error(int code, const std::string& msg) {
 static_assert(sizeof(fw_params) == sizeof(RenderParamsHost), "fw_params layout");
 static_assert(sizeof(ShapeRec) == 48 && sizeof(MeshRec) == 32 && sizeof(MatRec) == 32 && sizeof(TexRec) == 32, "rec sizes");
 
+// Render-time device state (path-state streams, sum / image buffers, stream, events).  It is independent of the
+// scene, ~1.2 GB at the default batch size, and expensive to allocate, so contexts are cached per device and
+// handed from one fw_scene to the next (fw_release_cached_memory frees them).
+struct RenderCtx {
+    int device = 0;
+    bool in_use = false;
+    PathState ps{};
+    size_t ps_cap = 0;
+    cudaStream_t stream = nullptr;
+    float* d_sum = nullptr;
+    unsigned char* d_rgb = nullptr;
+    size_t d_sum_pix = 0;
+    uint32_t* h_counters = nullptr;  // pinned
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+};
+static std::mutex g_ctx_mutex;
+static std::vector<RenderCtx*> g_ctx_cache;
+
 struct fw_scene {
     SceneDesc desc;
     HostFlat flat;
@@ -40,23 +60,17 @@ struct fw_scene {
     bool committed = false;  // uploaded to the device
     int device = 0;
     int sm_count = 148;
+    int bvh_blocks_per_sm = 4;
+    int extend_mode = 0;     // 0 = grid-stride extend (default), 1 = persistent dynamic-fetch variant (measured slower; FW_EXTEND_MODE)
+    int refill_lanes = FW_REFILL_LANES;
     DeviceScene dscene{};
     std::vector<void*> allocs;
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> texobjs;
     bool mat_present[MAT_NUM_QUEUES] = {false, false, false, false, false, false};
-    // render-time state (allocated lazily, reused across calls)
-    PathState ps{};
-    size_t ps_cap = 0;
-    size_t batch_paths = 0;  // 0 = default
-    cudaStream_t stream = nullptr;
-    float* d_sum = nullptr;
-    unsigned char* d_rgb = nullptr;
-    size_t d_sum_pix = 0;
-    uint32_t* h_counters = nullptr;  // pinned
+    RenderCtx* ctx = nullptr;  // render-time state, borrowed from the per-device cache at commit
+    size_t batch_paths = 0;    // 0 = default
     bool profiling = false;
-    std::vector<cudaEvent_t> ev_pool;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 };
 
 template <class T>
@@ -72,26 +86,64 @@ static int upload(fw_scene* sc, const std::vector<T>& host, const T** dev) {
     return FW_OK;
 }
 
+static void destroy_ctx(RenderCtx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
+    fr(c->ps.ray_o); fr(c->ps.ray_d); fr(c->ps.win_a); fr(c->ps.win_b); fr(c->ps.atten);
+    fr(c->ps.radiance); fr(c->ps.q_extend[0]); fr(c->ps.q_extend[1]); fr(c->ps.counters);
+    for (int k = 0; k < MAT_NUM_QUEUES; ++k) fr(c->ps.q_mat[k]);
+    fr(c->d_sum); fr(c->d_rgb);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int acquire_ctx(int device, RenderCtx** out) {
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mutex);
+        for (RenderCtx* c : g_ctx_cache)
+            if (c->device == device && !c->in_use) {
+                c->in_use = true;
+                *out = c;
+                return FW_OK;
+            }
+    }
+    RenderCtx* c = new RenderCtx();
+    c->device = device;
+    c->in_use = true;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_end);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_COUNTERS_PER_BOUNCE);
+    if (e != cudaSuccess) {
+        destroy_ctx(c);
+        return set_error(FW_ERR_CUDA, std::string("render context: ") + cudaGetErrorString(e));
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mutex);
+        g_ctx_cache.push_back(c);
+    }
+    *out = c;
+    return FW_OK;
+}
+
 static void release_device(fw_scene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
+    if (sc->ctx) {
+        cudaStreamSynchronize(sc->ctx->stream);
+        std::lock_guard<std::mutex> lk(g_ctx_mutex);
+        sc->ctx->in_use = false;  // back to the cache
+        sc->ctx = nullptr;
+    }
     for (auto t : sc->texobjs) cudaDestroyTextureObject(t);
     for (auto a : sc->arrays) cudaFreeArray(a);
     for (auto p : sc->allocs) cudaFree(p);
     sc->texobjs.clear(); sc->arrays.clear(); sc->allocs.clear();
-    auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
-    fr(sc->ps.ray_o); fr(sc->ps.ray_d); fr(sc->ps.hit_p); fr(sc->ps.hit_n); fr(sc->ps.hit_uv); fr(sc->ps.atten);
-    fr(sc->ps.radiance); fr(sc->ps.q_extend[0]); fr(sc->ps.q_extend[1]); fr(sc->ps.counters);
-    for (int k = 0; k < MAT_NUM_QUEUES; ++k) fr(sc->ps.q_mat[k]);
-    sc->ps_cap = 0;
-    fr(sc->d_sum); fr(sc->d_rgb);
-    sc->d_sum_pix = 0;
-    if (sc->h_counters) { cudaFreeHost(sc->h_counters); sc->h_counters = nullptr; }
-    for (auto e : sc->ev_pool) cudaEventDestroy(e);
-    sc->ev_pool.clear();
-    if (sc->ev_begin) { cudaEventDestroy(sc->ev_begin); sc->ev_begin = nullptr; }
-    if (sc->ev_end) { cudaEventDestroy(sc->ev_end); sc->ev_end = nullptr; }
-    if (sc->stream) { cudaStreamDestroy(sc->stream); sc->stream = nullptr; }
     sc->committed = false;
 }
 
@@ -234,10 +286,15 @@ int fw_scene_commit(fw_scene* sc, int device) {
     cudaDeviceProp prop;
     FW_CUDA(cudaGetDeviceProperties(&prop, device));
     sc->sm_count = prop.multiProcessorCount;
-    FW_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
-    FW_CUDA(cudaEventCreate(&sc->ev_begin));
-    FW_CUDA(cudaEventCreate(&sc->ev_end));
-    FW_CUDA(cudaMallocHost(&sc->h_counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_COUNTERS_PER_BOUNCE));
+    {
+        int nb = 0;
+        FW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extend_bvh_kernel, 128, 0));
+        sc->bvh_blocks_per_sm = std::max(nb, 1);
+    }
+    {
+        int crc = acquire_ctx(device, &sc->ctx);
+        if (crc != FW_OK) return crc;
+    }
 
     DeviceScene& D = sc->dscene;
     const HostFlat& F = sc->flat;
@@ -319,6 +376,16 @@ int fw_camera(const fw_params* p, float out[24]) {
     out[22] = out[23] = 0.0f;
     return FW_OK;
 }
+int fw_release_cached_memory(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    std::vector<RenderCtx*> keep;
+    for (RenderCtx* c : g_ctx_cache) {
+        if (c->in_use) keep.push_back(c);
+        else destroy_ctx(c);
+    }
+    g_ctx_cache.swap(keep);
+    return FW_OK;
+}
 int fw_set_profiling(fw_scene* sc, int enabled) {
     if (!sc) return set_error(FW_ERR_ARG, "null scene");
     sc->profiling = enabled != 0;
@@ -336,18 +403,21 @@ int fw_set_batch_paths(fw_scene* sc, uint64_t paths) {
 // wavefront orchestration
 // ----------------------------------------------------------------------------------------------------------
 static int ensure_path_state(fw_scene* sc, size_t cap) {
-    if (sc->ps_cap >= cap) return FW_OK;
+    RenderCtx* ctx = sc->ctx;
+    if (ctx->ps_cap >= cap) {
+        ctx->ps.cap = (uint32_t)ctx->ps_cap;
+        return FW_OK;
+    }
     auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
-    PathState& ps = sc->ps;
-    fr(ps.ray_o); fr(ps.ray_d); fr(ps.hit_p); fr(ps.hit_n); fr(ps.hit_uv); fr(ps.atten); fr(ps.radiance);
+    PathState& ps = ctx->ps;
+    fr(ps.ray_o); fr(ps.ray_d); fr(ps.win_a); fr(ps.win_b); fr(ps.atten); fr(ps.radiance);
     fr(ps.q_extend[0]); fr(ps.q_extend[1]); fr(ps.counters);
     for (int k = 0; k < MAT_NUM_QUEUES; ++k) fr(ps.q_mat[k]);
-    sc->ps_cap = 0;
+    ctx->ps_cap = 0;
     FW_CUDA(cudaMalloc(&ps.ray_o, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.ray_d, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.hit_p, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.hit_n, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.hit_uv, cap * sizeof(float2)));
+    FW_CUDA(cudaMalloc(&ps.win_a, cap * sizeof(float4)));
+    FW_CUDA(cudaMalloc(&ps.win_b, cap * sizeof(float2)));
     FW_CUDA(cudaMalloc(&ps.atten, cap * sizeof(float4) * FW_MAX_DEPTH));
     FW_CUDA(cudaMalloc(&ps.radiance, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.q_extend[0], cap * sizeof(uint32_t)));
@@ -355,7 +425,7 @@ static int ensure_path_state(fw_scene* sc, size_t cap) {
     for (int k = 0; k < MAT_NUM_QUEUES; ++k) FW_CUDA(cudaMalloc(&ps.q_mat[k], cap * sizeof(uint32_t)));
     FW_CUDA(cudaMalloc(&ps.counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_COUNTERS_PER_BOUNCE));
     ps.cap = (uint32_t)cap;
-    sc->ps_cap = cap;
+    ctx->ps_cap = cap;
     return FW_OK;
 }
 
@@ -365,12 +435,12 @@ struct RunTotals {
 };
 
 static int get_event(fw_scene* sc, size_t& next, cudaEvent_t* ev) {
-    if (next >= sc->ev_pool.size()) {
+    if (next >= sc->ctx->ev_pool.size()) {
         cudaEvent_t e;
         FW_CUDA(cudaEventCreate(&e));
-        sc->ev_pool.push_back(e);
+        sc->ctx->ev_pool.push_back(e);
     }
-    *ev = sc->ev_pool[next++];
+    *ev = sc->ctx->ev_pool[next++];
     return FW_OK;
 }
 
@@ -382,7 +452,7 @@ static inline unsigned grid_for(size_t n, unsigned threads, unsigned max_blocks)
 // One batch: raygen, up to FW_MAX_DEPTH+1 extend/shade rounds, accumulate into d_sum.
 static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 seed, bool use_bvh, float* d_sum,
                      cudaStream_t st, RunTotals& tot, size_t& ev_next) {
-    PathState& ps = sc->ps;
+    PathState& ps = sc->ctx->ps;
     const DeviceScene& S = sc->dscene;
     uint32_t N = b.npix * b.ns;
     const size_t counter_bytes = sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_COUNTERS_PER_BOUNCE;
@@ -391,6 +461,7 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
     raygen_kernel<<<grid_for(N, 256, sm * 8), 256, 0, st>>>(cam, b, seed, ps);
     tot.launches++;
     unsigned g_ext = grid_for(N, 128, sm * 16);
+    unsigned g_bvh = grid_for(N, 128, sm * (unsigned)sc->bvh_blocks_per_sm);  // persistent: one resident wave
     unsigned g_sh = grid_for(N, 256, sm * 8);
     for (uint32_t bounce = 0; bounce <= (uint32_t)FW_MAX_DEPTH; ++bounce) {
         uint32_t* row = ps.counters + bounce * FW_COUNTERS_PER_BOUNCE;
@@ -402,10 +473,12 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
             if ((rc = get_event(sc, ev_next, &e0)) != FW_OK || (rc = get_event(sc, ev_next, &e1)) != FW_OK) return rc;
             FW_CUDA(cudaEventRecord(e0, st));
         }
-        if (use_bvh)
-            extend_kernel<true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+        if (use_bvh && sc->extend_mode == 0)
+            extend_bvh_simple_kernel<<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+        else if (use_bvh)
+            extend_bvh_kernel<<<g_bvh, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, sc->refill_lanes);
         else
-            extend_kernel<false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+            extend_linear_kernel<<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
         if (sc->profiling) {
             FW_CUDA(cudaEventRecord(e1, st));
             tot.extend_events.emplace_back(e0, e1);
@@ -442,10 +515,10 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
     tot.launches++;
     FW_CUDA(cudaGetLastError());
     // ray statistics: extend inputs = N + sum over bounces of the re-queued paths
-    FW_CUDA(cudaMemcpyAsync(sc->h_counters, ps.counters, counter_bytes, cudaMemcpyDeviceToHost, st));
+    FW_CUDA(cudaMemcpyAsync(sc->ctx->h_counters, ps.counters, counter_bytes, cudaMemcpyDeviceToHost, st));
     FW_CUDA(cudaStreamSynchronize(st));
     tot.rays += N;
-    for (int bn = 0; bn < FW_MAX_DEPTH; ++bn) tot.rays += sc->h_counters[bn * FW_COUNTERS_PER_BOUNCE + 6];
+    for (int bn = 0; bn < FW_MAX_DEPTH; ++bn) tot.rays += sc->ctx->h_counters[bn * FW_COUNTERS_PER_BOUNCE + 6];
     return FW_OK;
 }
 
@@ -462,13 +535,15 @@ static int render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStrea
     size_t npix = (size_t)p->width * p->height;
     size_t cap = sc->batch_paths ? sc->batch_paths : ((size_t)1 << 22);
     if (const char* e = getenv("FW_BATCH_PATHS")) cap = std::max<size_t>(1024, strtoull(e, nullptr, 10));
+    if (const char* e = getenv("FW_EXTEND_MODE")) sc->extend_mode = atoi(e);
+    if (const char* e = getenv("FW_REFILL_LANES")) sc->refill_lanes = std::max(1, std::min(32, atoi(e)));
     cap = std::min<size_t>(cap, npix * std::max<uint32_t>(p->sample_count, 1));
     cap = std::max<size_t>(cap, 32);
     int rc;
     if ((rc = ensure_path_state(sc, cap)) != FW_OK) return rc;
     RunTotals tot;
     size_t ev_next = 0;
-    FW_CUDA(cudaEventRecord(sc->ev_begin, st));
+    FW_CUDA(cudaEventRecord(sc->ctx->ev_begin, st));
     // pixel tiles outer, sample chunks inner: every pixel's samples are accumulated in sample order
     size_t tile = std::min(npix, cap);
     for (size_t pix0 = 0; pix0 < npix; pix0 += tile) {
@@ -482,8 +557,8 @@ static int render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStrea
             if ((rc = run_batch(sc, cam, b, seed, p->use_bvh != 0, d_sum, st, tot, ev_next)) != FW_OK) return rc;
         }
     }
-    FW_CUDA(cudaEventRecord(sc->ev_end, st));
-    FW_CUDA(cudaEventSynchronize(sc->ev_end));
+    FW_CUDA(cudaEventRecord(sc->ctx->ev_end, st));
+    FW_CUDA(cudaEventSynchronize(sc->ctx->ev_end));
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->samples = (uint64_t)npix * p->sample_count;
@@ -491,7 +566,7 @@ static int render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStrea
         stats->launches = tot.launches;
         stats->extend_launches = tot.extend_launches;
         float ms = 0;
-        FW_CUDA(cudaEventElapsedTime(&ms, sc->ev_begin, sc->ev_end));
+        FW_CUDA(cudaEventElapsedTime(&ms, sc->ctx->ev_begin, sc->ctx->ev_end));
         stats->ms_device = ms;
         double me = 0;
         for (auto& pr : tot.extend_events) {
@@ -508,7 +583,7 @@ extern "C" {
 
 int fw_render_accumulate_device(fw_scene* sc, const fw_params* p, float* d_sum, void* cuda_stream, fw_stats* stats) {
     if (!sc || !d_sum) return set_error(FW_ERR_ARG, "null argument");
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : sc->stream;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : sc->ctx->stream;
     return render_into(sc, p, d_sum, st, stats);
 }
 
@@ -517,7 +592,7 @@ int fw_resolve_device(fw_scene* sc, const float* d_sum, uint32_t npix, uint32_t 
     if (!sc || !d_sum || !d_rgb || samples == 0) return set_error(FW_ERR_ARG, "bad argument");
     if (!sc->committed) return set_error(FW_ERR_STATE, "scene not committed");
     FW_CUDA(cudaSetDevice(sc->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : sc->stream;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : sc->ctx->stream;
     resolve_kernel<<<grid_for(npix, 256, sc->sm_count * 8), 256, 0, st>>>(d_sum, npix, (float)samples, gamma, d_rgb);
     FW_CUDA(cudaGetLastError());
     return FW_OK;
@@ -529,26 +604,26 @@ int fw_render(fw_scene* sc, const fw_params* p, uint8_t* rgb_out, float* sum_out
     FW_CUDA(cudaSetDevice(sc->device));
     size_t npix = (size_t)p->width * p->height;
     if (npix == 0) return set_error(FW_ERR_ARG, "empty image");
-    if (sc->d_sum_pix < npix) {
-        if (sc->d_sum) cudaFree(sc->d_sum);
-        if (sc->d_rgb) cudaFree(sc->d_rgb);
-        sc->d_sum = nullptr; sc->d_rgb = nullptr; sc->d_sum_pix = 0;
-        FW_CUDA(cudaMalloc(&sc->d_sum, npix * 3 * sizeof(float)));
-        FW_CUDA(cudaMalloc(&sc->d_rgb, npix * 3));
-        sc->d_sum_pix = npix;
+    if (sc->ctx->d_sum_pix < npix) {
+        if (sc->ctx->d_sum) cudaFree(sc->ctx->d_sum);
+        if (sc->ctx->d_rgb) cudaFree(sc->ctx->d_rgb);
+        sc->ctx->d_sum = nullptr; sc->ctx->d_rgb = nullptr; sc->ctx->d_sum_pix = 0;
+        FW_CUDA(cudaMalloc(&sc->ctx->d_sum, npix * 3 * sizeof(float)));
+        FW_CUDA(cudaMalloc(&sc->ctx->d_rgb, npix * 3));
+        sc->ctx->d_sum_pix = npix;
     }
-    FW_CUDA(cudaMemsetAsync(sc->d_sum, 0, npix * 3 * sizeof(float), sc->stream));
-    int rc = render_into(sc, p, sc->d_sum, sc->stream, stats);
+    FW_CUDA(cudaMemsetAsync(sc->ctx->d_sum, 0, npix * 3 * sizeof(float), sc->ctx->stream));
+    int rc = render_into(sc, p, sc->ctx->d_sum, sc->ctx->stream, stats);
     if (rc != FW_OK) return rc;
     if (rgb_out) {
-        resolve_kernel<<<grid_for(npix, 256, sc->sm_count * 8), 256, 0, sc->stream>>>(sc->d_sum, (uint32_t)npix,
-                                                                                     (float)p->samples, p->gamma, sc->d_rgb);
+        resolve_kernel<<<grid_for(npix, 256, sc->sm_count * 8), 256, 0, sc->ctx->stream>>>(sc->ctx->d_sum, (uint32_t)npix,
+                                                                                     (float)p->samples, p->gamma, sc->ctx->d_rgb);
         FW_CUDA(cudaGetLastError());
         if (stats) stats->launches++;
-        FW_CUDA(cudaMemcpyAsync(rgb_out, sc->d_rgb, npix * 3, cudaMemcpyDeviceToHost, sc->stream));
+        FW_CUDA(cudaMemcpyAsync(rgb_out, sc->ctx->d_rgb, npix * 3, cudaMemcpyDeviceToHost, sc->ctx->stream));
     }
-    if (sum_out) FW_CUDA(cudaMemcpyAsync(sum_out, sc->d_sum, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
-    FW_CUDA(cudaStreamSynchronize(sc->stream));
+    if (sum_out) FW_CUDA(cudaMemcpyAsync(sum_out, sc->ctx->d_sum, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, sc->ctx->stream));
+    FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     return FW_OK;
 }
 
@@ -565,11 +640,11 @@ int fw_primary_rays(fw_scene* sc, const fw_params* p, uint32_t sample, uint32_t 
     CameraRec cam = make_camera(hp);
     DevBuf o, d;
     TRY(o.alloc((size_t)n * 12)); TRY(d.alloc((size_t)n * 12));
-    primary_rays_probe<<<grid_for(n, 256, 4096), 256, 0, sc->stream>>>(cam, p->width, p->height, sample,
+    primary_rays_probe<<<grid_for(n, 256, 4096), 256, 0, sc->ctx->stream>>>(cam, p->width, p->height, sample,
                                                                        make_uint2((uint32_t)p->seed, (uint32_t)(p->seed >> 32)),
                                                                        pix_begin, n, o.as<float>(), d.as<float>());
     FW_CUDA(cudaGetLastError());
-    FW_CUDA(cudaStreamSynchronize(sc->stream));
+    FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     TRY(o.get(origins, (size_t)n * 12)); TRY(d.get(dirs, (size_t)n * 12));
     return FW_OK;
 }
@@ -594,15 +669,15 @@ int fw_first_hit(fw_scene* sc, int use_bvh, uint64_t seed, uint32_t n, const flo
     uint2 sd = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     unsigned g = grid_for(n, 128, 8192);
     if (use_bvh)
-        first_hit_probe<true><<<g, 128, 0, sc->stream>>>(sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
+        first_hit_probe<true><<<g, 128, 0, sc->ctx->stream>>>(sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
                                                          pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,
                                                          bounce ? dB.as<uint32_t>() : nullptr, out);
     else
-        first_hit_probe<false><<<g, 128, 0, sc->stream>>>(sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
+        first_hit_probe<false><<<g, 128, 0, sc->ctx->stream>>>(sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
                                                           pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,
                                                           bounce ? dB.as<uint32_t>() : nullptr, out);
     FW_CUDA(cudaGetLastError());
-    FW_CUDA(cudaStreamSynchronize(sc->stream));
+    FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     TRY(oObj.get(obj, (size_t)n * 4)); TRY(oPrim.get(prim, (size_t)n * 4)); TRY(oMat.get(material, (size_t)n * 4));
     TRY(oT.get(t, (size_t)n * 4)); TRY(oPt.get(point, (size_t)n * 12)); TRY(oN.get(normal, (size_t)n * 12));
     TRY(oUv.get(uv, (size_t)n * 8));
@@ -630,9 +705,9 @@ int fw_scatter_step(fw_scene* sc, uint32_t n, const int32_t* material, const flo
     ScatterProbeIO io{m.as<int>(), ro.as<float>(), rd.as<float>(), ht.as<float>(), hp.as<float>(), hn.as<float>(),
                       hu.as<float>(), un.as<float>(), nu, e.as<float>(), s.as<int>(), a.as<float>(), oo.as<float>(),
                       od.as<float>(), c.as<int>()};
-    scatter_step_probe<<<grid_for(n, 128, 4096), 128, 0, sc->stream>>>(sc->dscene, n, io);
+    scatter_step_probe<<<grid_for(n, 128, 4096), 128, 0, sc->ctx->stream>>>(sc->dscene, n, io);
     FW_CUDA(cudaGetLastError());
-    FW_CUDA(cudaStreamSynchronize(sc->stream));
+    FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     TRY(e.get(emit, (size_t)n * 12)); TRY(s.get(scattered, (size_t)n * 4)); TRY(a.get(atten, (size_t)n * 12));
     TRY(oo.get(out_o, (size_t)n * 12)); TRY(od.get(out_d, (size_t)n * 12)); TRY(c.get(consumed, (size_t)n * 4));
     return FW_OK;
@@ -644,9 +719,9 @@ int fw_env_sample(fw_scene* sc, uint32_t n, const float* dirs, float* out) {
     FW_CUDA(cudaSetDevice(sc->device));
     DevBuf d, o;
     TRY(d.put(dirs, (size_t)n * 12)); TRY(o.alloc((size_t)n * 12));
-    env_sample_probe<<<grid_for(n, 256, 4096), 256, 0, sc->stream>>>(sc->dscene, n, d.as<float>(), o.as<float>());
+    env_sample_probe<<<grid_for(n, 256, 4096), 256, 0, sc->ctx->stream>>>(sc->dscene, n, d.as<float>(), o.as<float>());
     FW_CUDA(cudaGetLastError());
-    FW_CUDA(cudaStreamSynchronize(sc->stream));
+    FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     return o.get(out, (size_t)n * 12);
 }
 int fw_texture_sample(fw_scene* sc, int texture, uint32_t n, const float* uv, const float* point, float* out) {
@@ -656,9 +731,9 @@ int fw_texture_sample(fw_scene* sc, int texture, uint32_t n, const float* uv, co
     FW_CUDA(cudaSetDevice(sc->device));
     DevBuf u, p, o;
     TRY(u.put(uv, (size_t)n * 8)); TRY(p.put(point, (size_t)n * 12)); TRY(o.alloc((size_t)n * 12));
-    texture_sample_probe<<<grid_for(n, 256, 4096), 256, 0, sc->stream>>>(sc->dscene, texture, n, u.as<float>(), p.as<float>(), o.as<float>());
+    texture_sample_probe<<<grid_for(n, 256, 4096), 256, 0, sc->ctx->stream>>>(sc->dscene, texture, n, u.as<float>(), p.as<float>(), o.as<float>());
     FW_CUDA(cudaGetLastError());
-    FW_CUDA(cudaStreamSynchronize(sc->stream));
+    FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     return o.get(out, (size_t)n * 12);
 }
 

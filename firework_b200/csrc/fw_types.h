@@ -50,7 +50,8 @@ struct MeshRec {  // 32 B
 };
 struct MatRec {  // 32 B
     int kind, tex;
-    float param, pad0;
+    float param;
+    int needs_uv;   // 1 if the material's texture tree contains an ImageTexture (the only uv consumer)
     float albedo[3], pad1;
 };
 struct TexRec {  // 32 B

@@ -534,6 +534,17 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
     out.shapes = desc.shapes;
     out.mats = desc.mats;
     out.texs = desc.texs;
+    {
+        // uv is read only by ImageTexture::sample (texture.rs:296-309); checker forwards it to its children
+        std::function<bool(int, int)> reads_uv = [&](int t, int depth) -> bool {
+            if (t < 0 || t >= (int)desc.texs.size() || depth > 64) return false;
+            const TexRec& r = desc.texs[t];
+            if (r.kind == TEX_IMAGE) return true;
+            if (r.kind == TEX_CHECKER) return reads_uv(r.a, depth + 1) || reads_uv(r.b, depth + 1);
+            return false;
+        };
+        for (MatRec& m : out.mats) m.needs_uv = reads_uv(m.tex, 0) ? 1 : 0;
+    }
 
     // Top-level tree occupies the front of nodes[]; it is appended after its size is known, so build
     // meshes into a side buffer first.
@@ -548,6 +559,10 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
             tb[t] = triangle_box(m.verts[m.indicies[3 * t]], m.verts[m.indicies[3 * t + 1]], m.verts[m.indicies[3 * t + 2]]);
         FlatBVH bvh;
         if (!build_bvh(tb, bvh, err)) return false;
+        if (bvh.max_depth >= 30) {
+            err = "mesh BVH deeper than the traversal stack";
+            return false;
+        }
         MeshRec rec;
         memset(&rec, 0, sizeof(rec));
         rec.node_root = (int)(mesh_nodes.size() / 2);  // relative; rebased below
@@ -692,6 +707,10 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
     // top-level BVH (bvh.rs:79-98), always built: linear-scan renders simply do not use it
     FlatBVH top;
     if (!build_bvh(out.obj_aabb, top, err, &obj_unbounded)) return false;
+    if (top.max_depth >= 30) {
+        err = "top-level BVH deeper than the traversal stack";
+        return false;
+    }
     out.top_items = top.items;
     out.top_depth = top.max_depth;
     out.top_nodes = (int)(top.nodes.size() / 2);

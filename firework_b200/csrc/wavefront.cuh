@@ -3,7 +3,9 @@
 //
 // Path p of a batch covers pixel  pix0 + p % npix  and sample  s0 + p / npix  (implicit mapping: no id arrays).
 // Per-path state lives in HBM as SoA float4 streams; per-bounce queues hold path ids, compacted with
-// warp ballot / popc so that one atomicAdd per warp per queue reserves the slots.
+// warp ballot / popc so that one atomicAdd per warp per queue reserves the slots.  extend publishes only the
+// winning (t, object, primitive, barycentrics); the shade kernel that consumes a path rebuilds point / normal /
+// uv (finalize_hit) in registers.
 #pragma once
 #include "intersect.cuh"
 #include "shade.cuh"
@@ -11,14 +13,13 @@
 namespace fw {
 
 constexpr int FW_MAX_DEPTH = 10;          // render.rs:21  `depth < 10`
-constexpr int FW_COUNTERS_PER_BOUNCE = 8; // [0..5] material queues (MatKind), [6] next extend queue, [7] spare
+constexpr int FW_COUNTERS_PER_BOUNCE = 8; // [0..5] material queues (MatKind), [6] next extend queue, [7] extend work cursor
 
 struct PathState {
     float4* ray_o;     // [cap] origin.xyz
     float4* ray_d;     // [cap] direction.xyz (never normalised: ray.rs)
-    float4* hit_p;     // [cap] point.xyz, t
-    float4* hit_n;     // [cap] normal.xyz, asfloat(material)
-    float2* hit_uv;    // [cap]
+    float4* win_a;     // [cap] winning hit: t, asfloat(object), asfloat(primitive), b0
+    float2* win_b;     // [cap] b1, b2 (triangle barycentrics)
     float4* atten;     // [FW_MAX_DEPTH][cap] attenuation chain (see fold_radiance)
     float4* radiance;  // [cap] finished path radiance
     uint32_t* q_extend[2];             // ping-pong extend queues
@@ -87,13 +88,110 @@ FW_DEV void warp_enqueue(uint32_t* const* queues, uint32_t* counters, int mine, 
     }
 }
 
-// extend: closest hit for every queued path; writes the hit record and sorts the path into its
-// material's shade queue (or the miss queue).
-template <bool USE_BVH>
-__global__ void __launch_bounds__(128) extend_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
-                                                     const uint32_t* __restrict__ q_in,
-                                                     const uint32_t* __restrict__ count_in, uint32_t n_direct,
-                                                     uint32_t* counters_out) {
+// extend: closest hit for every queued path; writes the winning (t, object, primitive, barycentrics) and
+// sorts the path into its material's shade queue (or the miss queue).  The full hit record is rebuilt by the
+// shade kernel that consumes it (finalize_hit), so it never travels through HBM.
+//
+// BVH scenes: persistent warps with dynamic ray fetch.  A lane whose ray has finished parks until the warp
+// reaches the converged top of the loop, where finished lanes publish their result (one ballot per material
+// queue) and free lanes pull new rays from the queue with one atomicAdd per warp.  While work remains the
+// traversal burst ends as soon as fewer than FW_REFILL_LANES lanes are still walking, so a few long rays do
+// not hold 31 idle lanes hostage.
+constexpr int FW_REFILL_LANES = 22;
+
+FW_DEV void store_winner(const PathState& ps, uint32_t path, const Winner& w) {
+    if (w.found) {
+        ps.win_a[path] = make_float4(w.t, __int_as_float(w.obj), __int_as_float(w.h.prim), w.h.b0);
+        ps.win_b[path] = make_float2(w.h.b1, w.h.b2);
+    } else {
+        ps.win_a[path] = make_float4(0.0f, __int_as_float(-1), 0.0f, 0.0f);
+    }
+}
+FW_DEV Winner load_winner(const PathState& ps, uint32_t path) {
+    float4 a = ps.win_a[path];
+    float2 b = ps.win_b[path];
+    Winner w;
+    w.found = true;
+    w.t = a.x; w.obj = __float_as_int(a.y); w.rank = 0;
+    w.h.t = a.x; w.h.prim = __float_as_int(a.z); w.h.b0 = a.w; w.h.b1 = b.x; w.h.b2 = b.y;
+    return w;
+}
+FW_DEV int winner_queue(const DeviceScene& S, const Winner& w) {
+    if (!w.found) return MAT_MISS;
+    return __ldg(&S.mats[winner_material(S, w.obj, w.h.prim)].kind);
+}
+
+__global__ void __launch_bounds__(128) extend_bvh_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                         const uint32_t* __restrict__ q_in,
+                                                         const uint32_t* __restrict__ count_in, uint32_t n_direct,
+                                                         uint32_t* counters_out, int refill_lanes) {
+    const uint32_t total = count_in ? *count_in : n_direct;
+    uint32_t* cursor = counters_out + 7;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    enum { EMPTY = 0, ACTIVE = 1, DONE = 2 };
+    int state = EMPTY;
+    uint32_t path = 0;
+    bool more = true;
+    RngKey key{seed, 0u, 0u, bounce};
+    float3 o = f3(0.0f, 0.0f, 0.0f), d = f3(0.0f, 0.0f, 1.0f);
+    BvhWalker<false> walker;
+    TopLeaf<false> leaf(S, o, d, key, nullptr);
+    for (;;) {
+        // ---- converged: publish finished rays
+        unsigned done = __ballot_sync(0xffffffffu, state == DONE);
+        if (done) {
+            int mine = -1;
+            if (state == DONE) {
+                store_winner(ps, path, leaf.w);
+                mine = winner_queue(S, leaf.w);
+                state = EMPTY;
+            }
+            warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
+        }
+        // ---- converged: refill free lanes
+        unsigned empty = __ballot_sync(0xffffffffu, state == EMPTY);
+        if (empty && more) {
+            int n = __popc(empty);
+            int leader = __ffs(empty) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)n);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + (uint32_t)n >= total) more = false;
+            if (state == EMPTY) {
+                uint32_t i = base + __popc(empty & lt);
+                if (i < total) {
+                    path = q_in ? q_in[i] : i;
+                    float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
+                    o = f3(ro); d = f3(rd);
+                    batch_path(b, path, key.pixel, key.sample);
+                    leaf.o = o; leaf.d = d;
+                    leaf.w.found = false; leaf.w.t = 0.0f; leaf.w.obj = -1; leaf.w.rank = -1;
+                    leaf.bnd = FW_FLT_MAX;
+                    state = walker.init(S.nodes, 0, o, d, 0.001f, 2e9f, nullptr) ? ACTIVE : DONE;
+                }
+            }
+        }
+        unsigned active = __ballot_sync(0xffffffffu, state == ACTIVE);
+        if (active == 0u) {
+            if (__ballot_sync(0xffffffffu, state == DONE)) continue;
+            break;
+        }
+        // ---- traversal burst
+        int keep = more ? min(__popc(active), refill_lanes) : 1;
+        do {
+            if (state == ACTIVE) {
+                if (!walker.step(S.nodes, leaf, nullptr)) state = DONE;
+            }
+        } while (__popc(__ballot_sync(0xffffffffu, state == ACTIVE)) >= keep);
+    }
+}
+
+// A/B variant: one ray per thread per grid-stride iteration, run to completion (no dynamic fetch).
+__global__ void __launch_bounds__(128) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                                const uint32_t* __restrict__ q_in,
+                                                                const uint32_t* __restrict__ count_in, uint32_t n_direct,
+                                                                uint32_t* counters_out) {
     uint32_t total = count_in ? *count_in : n_direct;
     uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
@@ -103,18 +201,48 @@ __global__ void __launch_bounds__(128) extend_kernel(DeviceScene S, PathState ps
         if (i < total) {
             path = q_in ? q_in[i] : i;
             float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
-            uint32_t pixel, sample;
-            batch_path(b, path, pixel, sample);
-            RngKey key{seed, pixel, sample, bounce};
-            HitRecord rec;
-            if (scene_closest_hit<USE_BVH, false>(S, f3(ro), f3(rd), key, rec, nullptr)) {
-                ps.hit_p[path] = make_float4(rec.point.x, rec.point.y, rec.point.z, rec.t);
-                ps.hit_n[path] = make_float4(rec.normal.x, rec.normal.y, rec.normal.z, __int_as_float(rec.material));
-                ps.hit_uv[path] = rec.uv;
-                mine = __ldg(&S.mats[rec.material].kind);
-            } else {
-                mine = MAT_MISS;
+            float3 o = f3(ro), d = f3(rd);
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            TopLeaf<false> leaf(S, o, d, key, nullptr);
+            bvh_traverse<TopLeaf<false>, false>(S.nodes, 0, o, d, 0.001f, 2e9f, leaf, nullptr);
+            store_winner(ps, path, leaf.w);
+            mine = winner_queue(S, leaf.w);
+        }
+        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
+    }
+}
+
+// Linear-scan scenes (Renderer.use_bvh == false, scene.rs:137-149): every ray tests every object in scene
+// order, so there is no traversal-length divergence to balance; a plain grid-stride loop.
+__global__ void __launch_bounds__(128) extend_linear_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                            const uint32_t* __restrict__ q_in,
+                                                            const uint32_t* __restrict__ count_in, uint32_t n_direct,
+                                                            uint32_t* counters_out) {
+    uint32_t total = count_in ? *count_in : n_direct;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        uint32_t i = base + threadIdx.x;
+        int mine = -1;
+        uint32_t path = 0;
+        if (i < total) {
+            path = q_in ? q_in[i] : i;
+            float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
+            float3 o = f3(ro), d = f3(rd);
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            Winner w;
+            w.found = false; w.t = 0.0f; w.obj = -1; w.rank = -1;
+            float closest = 2e9f;
+            for (int obj = 0; obj < S.n_objects; ++obj) {
+                ObjHit h;
+                if (object_test<false>(S, obj, o, d, 0.001f, closest, FW_FLT_MAX, key, h, nullptr)) {
+                    closest = h.t;
+                    w.found = true; w.t = h.t; w.obj = obj; w.rank = obj; w.h = h;
+                }
             }
+            store_winner(ps, path, w);
+            mine = winner_queue(S, w);
         }
         warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
     }
@@ -152,9 +280,11 @@ __global__ void __launch_bounds__(256) shade_emissive_kernel(DeviceScene S, Path
     const uint32_t* q = ps.q_mat[MAT_EMISSIVE];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         uint32_t path = q[i];
-        float4 hp = ps.hit_p[path], hn = ps.hit_n[path];
-        int tex = __ldg(&S.mats[__float_as_int(hn.w)].tex);
-        float3 emit = texture_sample(S, tex, ps.hit_uv[path], f3(hp));
+        Winner w = load_winner(ps, path);
+        HitRecord rec;
+        finalize_hit(S, w, f3(ps.ray_o[path]), f3(ps.ray_d[path]), rec, true);
+        int tex = __ldg(&S.mats[rec.material].tex);
+        float3 emit = texture_sample(S, tex, rec.uv, rec.point);
         float3 c = fold_radiance(ps, path, bounce, emit);
         ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
     }
@@ -175,23 +305,27 @@ __global__ void __launch_bounds__(256) shade_scatter_kernel(DeviceScene S, PathS
         uint32_t path = 0;
         if (i < total) {
             path = q[i];
-            float4 hp = ps.hit_p[path], hn = ps.hit_n[path];
-            float3 point = f3(hp), normal = f3(hn);
-            const float4* mq = reinterpret_cast<const float4*>(&S.mats[__float_as_int(hn.w)]);
-            float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);  // (kind, tex, param, -), (albedo, -)
+            float3 in_o = f3(ps.ray_o[path]), in_d = f3(ps.ray_d[path]);
+            Winner w = load_winner(ps, path);
+            int material = winner_material(S, w.obj, w.h.prim);
+            const float4* mq = reinterpret_cast<const float4*>(&S.mats[material]);
+            float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);  // (kind, tex, param, needs_uv), (albedo, -)
+            HitRecord rec;
+            finalize_hit(S, w, in_o, in_d, rec, __float_as_int(m0.w) != 0);
+            float3 point = rec.point, normal = rec.normal;
             uint32_t pixel, sample;
             batch_path(b, path, pixel, sample);
             RngKey key{seed, pixel, sample, bounce};
             PhiloxStream rng(key, STREAM_SCATTER);
             ScatterOut out;
             if (MAT == MAT_LAMBERTIAN) {
-                scatter_lambertian(S, __float_as_int(m0.y), point, normal, ps.hit_uv[path], rng, out);
+                scatter_lambertian(S, __float_as_int(m0.y), point, normal, rec.uv, rng, out);
             } else if (MAT == MAT_METAL) {
-                scatter_metal(f3(m1), m0.z, f3(ps.ray_d[path]), point, normal, rng, out);
+                scatter_metal(f3(m1), m0.z, in_d, point, normal, rng, out);
             } else if (MAT == MAT_DIELECTRIC) {
-                scatter_dielectric(m0.z, f3(ps.ray_d[path]), point, normal, rng, out);
+                scatter_dielectric(m0.z, in_d, point, normal, rng, out);
             } else {
-                scatter_isotropic(S, __float_as_int(m0.y), point, ps.hit_uv[path], rng, out);
+                scatter_isotropic(S, __float_as_int(m0.y), point, rec.uv, rng, out);
             }
             if (out.scattered) {
                 ps.ray_o[path] = make_float4(out.origin.x, out.origin.y, out.origin.z, 0.0f);

@@ -136,6 +136,9 @@ int fw_device_count(void);
 int fw_measure_peaks(int device, double* fp32_tflops, double* l2_gbs, int* sm_count, int* sm_clock_khz);
 /* Per-kernel CUDA-event profiling of extend launches (adds synchronisation; off by default). */
 int fw_set_profiling(fw_scene* scene, int enabled);
+/* Render-time device buffers (path-state streams, ~1.2 GB at the default batch size) are cached per device
+ * across scenes; this frees every cached context that is not in use. */
+int fw_release_cached_memory(void);
 /* Maximum number of paths in flight per batch (0 = default). */
 int fw_set_batch_paths(fw_scene* scene, uint64_t paths);
 
