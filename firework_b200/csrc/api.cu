@@ -300,7 +300,7 @@ int fw_scene_commit(fw_scene* sc, int device) {
     const HostFlat& F = sc->flat;
     int rc;
 #define UP(field) if ((rc = upload(sc, F.field, &D.field)) != FW_OK) return rc
-    UP(nodes); UP(top_items); UP(obj_posr); UP(obj_meta); UP(obj_rot); UP(obj_irot); UP(shapes); UP(meshes);
+    UP(nodes); UP(top_items); UP(leaf_posr); UP(leaf_meta); UP(obj_posr); UP(obj_meta); UP(obj_rot); UP(obj_irot); UP(shapes); UP(meshes);
     UP(tri_verts); UP(tri_normals); UP(tri_uvs); UP(mats); UP(texs);
 #undef UP
     std::vector<ImageRec> images(std::max<size_t>(sc->desc.assets.size(), 1));
@@ -328,6 +328,8 @@ int fw_scene_commit(fw_scene* sc, int device) {
     D.n_nodes = (int)(F.nodes.size() / 2);
     D.top_root_is_valid = 1;
     D.has_medium = F.has_medium ? 1 : 0;
+    D.nan_bvh_obj = F.nan_bvh_obj; D.nan_bvh_prim = F.nan_bvh_prim;
+    D.nan_lin_obj = F.nan_lin_obj; D.nan_lin_prim = F.nan_lin_prim;
     for (const MatRec& m : F.mats) sc->mat_present[m.kind] = true;
     sc->committed = true;
     return FW_OK;
@@ -473,12 +475,42 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
             if ((rc = get_event(sc, ev_next, &e0)) != FW_OK || (rc = get_event(sc, ev_next, &e1)) != FW_OK) return rc;
             FW_CUDA(cudaEventRecord(e0, st));
         }
-        if (use_bvh && sc->extend_mode == 0)
-            extend_bvh_simple_kernel<<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
-        else if (use_bvh)
+        if (use_bvh && getenv("FW_DEBUG_STEPS")) {
+            // debug: per-path box-test counts, worst path of every bounce printed to stderr
+            static uint32_t* d_steps = nullptr;
+            static size_t d_steps_cap = 0;
+            if (d_steps_cap < ps.cap) {
+                if (d_steps) cudaFree(d_steps);
+                FW_CUDA(cudaMalloc(&d_steps, (size_t)ps.cap * 4));
+                d_steps_cap = ps.cap;
+            }
+            FW_CUDA(cudaMemsetAsync(d_steps, 0, (size_t)ps.cap * 4, st));
+            extend_bvh_debug_kernel<<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, d_steps);
+            FW_CUDA(cudaStreamSynchronize(st));
+            std::vector<uint32_t> hs(ps.cap);
+            FW_CUDA(cudaMemcpy(hs.data(), d_steps, (size_t)ps.cap * 4, cudaMemcpyDeviceToHost));
+            size_t worst = 0;
+            unsigned long long sum = 0;
+            for (size_t i = 0; i < N; ++i) { sum += hs[i]; if (hs[i] > hs[worst]) worst = i; }
+            float4 ro, rd;
+            FW_CUDA(cudaMemcpy(&ro, ps.ray_o + worst, 16, cudaMemcpyDeviceToHost));
+            FW_CUDA(cudaMemcpy(&rd, ps.ray_d + worst, 16, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[fw debug] bounce %u: box tests total %llu, worst path %zu (pixel %zu sample %zu): %u tests, o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g)\n",
+                    bounce, sum, worst, (size_t)b.pix0 + worst % b.npix, (size_t)b.s0 + worst / b.npix, hs[worst], ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
+        } else if (use_bvh && sc->extend_mode == 0) {
+            if (sc->flat.has_medium_mesh)
+                extend_bvh_simple_kernel<true, true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+            else
+                extend_bvh_simple_kernel<false, true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+        } else if (use_bvh && sc->extend_mode == 2) {
+            extend_bvh_simple_kernel<true, false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+        } else if (use_bvh) {
             extend_bvh_kernel<<<g_bvh, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, sc->refill_lanes);
-        else
-            extend_linear_kernel<<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+        } else if (sc->flat.has_mesh) {
+            extend_linear_kernel<true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+        } else {
+            extend_linear_kernel<false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+        }
         if (sc->profiling) {
             FW_CUDA(cudaEventRecord(e1, st));
             tot.extend_events.emplace_back(e0, e1);

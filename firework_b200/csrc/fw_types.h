@@ -80,6 +80,8 @@ struct EnvRec {
 struct DeviceScene {
     const float4* nodes;       // all trees; top-level root at node 0
     const int* top_items;      // object ids in top-level DFS leaf order (rank = tie-break key, bvh.rs:128,141)
+    const float4* leaf_posr;   // obj_posr reordered by top-level DFS leaf rank (no indirection in the leaf loop)
+    const int4* leaf_meta;     // obj_meta reordered by rank; .w = object id
     const float4* obj_posr;    // per object: (position.xyz, sphere radius or 0)
     const int4* obj_meta;      // per object: (kind | flags, material, shape index, 0)
     const float4* obj_rot;     // per object: 3 x float4 = columns of rotation_mat
@@ -97,6 +99,9 @@ struct DeviceScene {
     int n_nodes;
     int top_root_is_valid;     // 0 if the top-level BVH was not built (linear scenes may still build it)
     int has_medium;
+    // Closest-hit answer for a ray whose direction is NaN in all three components (see nan_direction_winner):
+    // object id (-1 = miss) and primitive (mesh: last triangle slot, Rect3d: last face), for BVH and linear roots.
+    int nan_bvh_obj, nan_bvh_prim, nan_lin_obj, nan_lin_prim;
 };
 
 struct CameraRec {  // camera.rs:7-16

@@ -701,6 +701,8 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
             out.obj_irot.push_back(float4{Ri.c[c].x, Ri.c[c].y, Ri.c[c].z, 0});
         }
         if (s.kind == SH_MEDIUM) out.has_medium = true;
+        if (s.kind == SH_MESH) out.has_mesh = true;
+        if (s.kind == SH_MEDIUM && desc.shapes[s.i0].kind == SH_MESH) out.has_mesh = out.has_medium_mesh = true;
         obj_unbounded[i] = shape_unbounded(o.shape) ? 1 : 0;
     }
 
@@ -712,12 +714,45 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         return false;
     }
     out.top_items = top.items;
+    for (int obj : top.items) {
+        out.leaf_posr.push_back(out.obj_posr[obj]);
+        int4 m = out.obj_meta[obj];
+        m.w = obj;
+        out.leaf_meta.push_back(m);
+    }
     out.top_depth = top.max_depth;
     out.top_nodes = (int)(top.nodes.size() / 2);
     out.nodes = top.nodes;
     if ((out.nodes.size() / 2) % 2) {  // keep every tree's root on an even node index
         out.nodes.push_back(float4{INFINITY, INFINITY, INFINITY, as_float(~0)});
         out.nodes.push_back(float4{-INFINITY, -INFINITY, -INFINITY, as_float(0)});
+    }
+    // A ray with an all-NaN direction (e.g. after scattering off a zero-length interpolated normal) passes every
+    // slab test (f32::max/min ignore NaN, aabb.rs:46-48) and is then "hit" by every primitive whose rejection
+    // tests are all comparisons (NaN compares false): AARect (rect.rs:51,55), Triangle (mesh.rs:170-186), Disk,
+    // Cone; Sphere, Cylinder and ConstantMedium reject it (their accept test is a comparison).  bvh.rs:128,141
+    // (`left.t < right.t` false -> right) and scene.rs:142 (NaN `closest` never rejects) both make the LAST
+    // accepting item win, so the answer does not depend on the ray and is precomputed here; the kernels return it
+    // directly instead of walking the entire tree (milliseconds for one path).
+    {
+        auto accepts = [&](int obj, int& prim) -> bool {
+            const ShapeRec& sh = desc.shapes[desc.objects[obj].shape];
+            prim = 0;
+            switch (sh.kind) {
+                case SH_RECT: case SH_DISK: case SH_CONE: return true;
+                case SH_RECT3D: prim = sh.i1 - 1; return sh.i1 > 0;
+                case SH_MESH: prim = out.meshes[sh.i0].tri_count - 1; return true;   // last triangle slot
+                default: return false;
+            }
+        };
+        for (int rank = (int)out.top_items.size() - 1; rank >= 0; --rank) {
+            int prim;
+            if (accepts(out.top_items[rank], prim)) { out.nan_bvh_obj = out.top_items[rank]; out.nan_bvh_prim = prim; break; }
+        }
+        for (int obj = (int)desc.objects.size() - 1; obj >= 0; --obj) {
+            int prim;
+            if (accepts(obj, prim)) { out.nan_lin_obj = obj; out.nan_lin_prim = prim; break; }
+        }
     }
     int base = (int)(out.nodes.size() / 2);
     // append mesh trees, rebasing interior child links and mesh roots

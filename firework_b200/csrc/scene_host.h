@@ -71,8 +71,8 @@ bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& er
 struct HostFlat {
     std::vector<float4> nodes;
     std::vector<int> top_items;
-    std::vector<float4> obj_posr;
-    std::vector<int4> obj_meta;
+    std::vector<float4> obj_posr, leaf_posr;
+    std::vector<int4> obj_meta, leaf_meta;
     std::vector<float4> obj_rot, obj_irot;
     std::vector<Box> obj_aabb;  // world boxes (scene.rs:167-212), kept for tests / stats
     std::vector<ShapeRec> shapes;
@@ -84,6 +84,9 @@ struct HostFlat {
     int top_depth = 0;
     int top_nodes = 0;
     bool has_medium = false;
+    int nan_bvh_obj = -1, nan_bvh_prim = 0, nan_lin_obj = -1, nan_lin_prim = 0;
+    bool has_mesh = false;          // some object is (or wraps) a TriangleMesh
+    bool has_medium_mesh = false;   // some ConstantMedium wraps a TriangleMesh
 };
 bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err);
 

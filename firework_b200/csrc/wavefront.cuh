@@ -187,7 +187,38 @@ __global__ void __launch_bounds__(128) extend_bvh_kernel(DeviceScene S, PathStat
     }
 }
 
-// A/B variant: one ray per thread per grid-stride iteration, run to completion (no dynamic fetch).
+// BVH scenes: one ray per thread per grid-stride iteration, unified two-level traversal run to completion.
+// Consecutive lanes hold consecutive pixels (primary) / consecutive queue entries, which keeps warps coherent;
+// the persistent dynamic-fetch variant above was measured 10-30 % slower on every scene because refilling
+// mixes unrelated rays into a warp (profiles/r01_extend_variants.md).
+// Debug twin of the BVH extend: also records the number of box tests each path needed (FW_DEBUG_STEPS=1).
+__global__ void __launch_bounds__(128) extend_bvh_debug_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                               const uint32_t* __restrict__ q_in,
+                                                               const uint32_t* __restrict__ count_in, uint32_t n_direct,
+                                                               uint32_t* counters_out, uint32_t* steps) {
+    uint32_t total = count_in ? *count_in : n_direct;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        uint32_t i = base + threadIdx.x;
+        int mine = -1;
+        uint32_t path = 0;
+        if (i < total) {
+            path = q_in ? q_in[i] : i;
+            float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            Winner w;
+            Counters cnt{0, 0};
+            trace_unified<true, true>(S, o, d, key, w, &cnt);
+            steps[path] = (uint32_t)cnt.node_tests;
+            store_winner(ps, path, w);
+            mine = winner_queue(S, w);
+        }
+        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
+    }
+}
+
+template <bool NESTED, bool UNIFIED>
 __global__ void __launch_bounds__(128) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
                                                                 const uint32_t* __restrict__ q_in,
                                                                 const uint32_t* __restrict__ count_in, uint32_t n_direct,
@@ -204,10 +235,16 @@ __global__ void __launch_bounds__(128) extend_bvh_simple_kernel(DeviceScene S, P
             float3 o = f3(ro), d = f3(rd);
             RngKey key{seed, 0u, 0u, bounce};
             batch_path(b, path, key.pixel, key.sample);
-            TopLeaf<false> leaf(S, o, d, key, nullptr);
-            bvh_traverse<TopLeaf<false>, false>(S.nodes, 0, o, d, 0.001f, 2e9f, leaf, nullptr);
-            store_winner(ps, path, leaf.w);
-            mine = winner_queue(S, leaf.w);
+            Winner w;
+            if (UNIFIED) {
+                trace_unified<false, NESTED>(S, o, d, key, w, nullptr);
+            } else {
+                TopLeaf<false> leaf(S, o, d, key, nullptr);
+                bvh_traverse<TopLeaf<false>, false>(S.nodes, 0, o, d, 0.001f, 2e9f, leaf, nullptr);
+                w = leaf.w;
+            }
+            store_winner(ps, path, w);
+            mine = winner_queue(S, w);
         }
         warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
     }
@@ -215,6 +252,8 @@ __global__ void __launch_bounds__(128) extend_bvh_simple_kernel(DeviceScene S, P
 
 // Linear-scan scenes (Renderer.use_bvh == false, scene.rs:137-149): every ray tests every object in scene
 // order, so there is no traversal-length divergence to balance; a plain grid-stride loop.
+// NESTED: the scene contains a TriangleMesh (its own BVH is walked inside the object test).
+template <bool NESTED>
 __global__ void __launch_bounds__(128) extend_linear_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
                                                             const uint32_t* __restrict__ q_in,
                                                             const uint32_t* __restrict__ count_in, uint32_t n_direct,
@@ -234,9 +273,11 @@ __global__ void __launch_bounds__(128) extend_linear_kernel(DeviceScene S, PathS
             Winner w;
             w.found = false; w.t = 0.0f; w.obj = -1; w.rank = -1;
             float closest = 2e9f;
+            if (nan_direction(d)) nan_direction_winner(S.nan_lin_obj, S.nan_lin_prim, w);
+            else
             for (int obj = 0; obj < S.n_objects; ++obj) {
                 ObjHit h;
-                if (object_test<false>(S, obj, o, d, 0.001f, closest, FW_FLT_MAX, key, h, nullptr)) {
+                if (object_test<false, NESTED>(S, obj, o, d, 0.001f, closest, FW_FLT_MAX, key, h, nullptr)) {
                     closest = h.t;
                     w.found = true; w.t = h.t; w.obj = obj; w.rank = obj; w.h = h;
                 }

@@ -114,6 +114,29 @@ def test_first_hit_ties_and_coincident_geometry(scenes):
     ns.close()
 
 
+@pytest.mark.parametrize("name", ["teapot", "suzanne", "cornell_box", "conics", "conics_cli", "part2_all",
+                                  "random_spheres", "volume"])
+def test_nan_direction_rays_follow_the_reference(scenes, name):
+    """A ray whose direction is NaN (it happens: scattering off a zero interpolated normal) passes every slab test
+    and is accepted by every comparison-rejecting primitive; the reference's merge rules then make the LAST item in
+    DFS / scene order win.  The CUDA path answers from a precomputed table instead of walking the whole tree; the
+    oracle simply executes the reference logic."""
+    ns, orc = scenes(name)
+    cfg = CONFIGS[name]
+    n = 64
+    rng = np.random.default_rng(9)
+    o = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    o[n // 2:] = np.nan                       # later bounces: origin is NaN as well
+    d = np.full((n, 3), np.nan, np.float32)
+    g = ns.first_hit(o, d, cfg.use_bvh)
+    r = orc.first_hit(o, d)
+    assert np.array_equal(g["obj"], r["obj"]) and np.array_equal(g["prim"], r["prim"])
+    assert np.array_equal(g["material"], r["material"])
+    hit = r["obj"] >= 0
+    assert np.isnan(g["t"][hit]).all() and np.isnan(r["t"][hit]).all()
+    assert np.array_equal(np.isnan(g["normal"]), np.isnan(r["normal"]))
+
+
 @pytest.mark.parametrize("name", ["random_spheres", "cornell_box", "earth", "part2_all", "volume", "hdri_test"])
 def test_scatter_step_gate(scenes, name):
     """Gate 2: emit + one scatter step of every material in the scene, identical explicit uniforms, within 1e-5."""

@@ -1,0 +1,17 @@
+import os, sys, gzip
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from firework_b200.engine import NativeScene
+from firework_b200.scenes import CONFIGS, SCENE_DIR
+ASSETS = os.path.join(SCENE_DIR, "assets")
+cfg = CONFIGS["teapot"]; p = cfg.path()
+text = gzip.open(p, "rt").read()
+ns = NativeScene(text, asset_dir=ASSETS); ns.set_profiling(True)
+r = cfg.renderer(width=1920, height=1080, samples=8, seed=1)
+for rep in range(2):
+    for s0 in range(0, 8):
+        _, _, st = ns.render(r.params(sample_begin=s0, sample_count=1), want_sum=False)
+        print(rep, "sample", s0, f"device {st['ms_device']:.2f} extend {st['ms_extend']:.2f} rays {st['rays']}", flush=True)
+for seed in (1, 2, 3):
+    r = cfg.renderer(width=1920, height=1080, samples=8, seed=seed)
+    _, _, st = ns.render(r.params(), want_sum=False)
+    print("seed", seed, f"device {st['ms_device']:.2f} extend {st['ms_extend']:.2f} rays {st['rays']}", flush=True)
