@@ -132,11 +132,12 @@ def run_cpu(cfg, doc, assets, width, height, spp, target_seconds, seed):
     reduced spp where needed). Returns (Msamples/s, Mrays/s, stats, sample description)."""
     orc = oracle_scene_for(doc, cfg, assets)
     r = cfg.renderer(width=width, height=height, samples=spp, seed=seed)
+    threads = len(os.sched_getaffinity(0))   # all host cores (torchrun exports OMP_NUM_THREADS=1: override it)
     probe_spp = 1
-    _, _, st = orc.render(r.params(sample_begin=0, sample_count=probe_spp), want_rgb=False)
+    _, _, st = orc.render(r.params(sample_begin=0, sample_count=probe_spp), want_rgb=False, threads=threads)
     rate = st["samples"] / max(st["seconds"], 1e-6)
     n = int(max(1, min(spp, target_seconds * rate / (width * height))))
-    _, _, st = orc.render(r.params(sample_begin=0, sample_count=n), want_rgb=False)
+    _, _, st = orc.render(r.params(sample_begin=0, sample_count=n), want_rgb=False, threads=threads)
     return st["samples"] / st["seconds"] / 1e6, st["rays"] / st["seconds"] / 1e6, st, f"{width}x{height} x {n} of {spp} spp"
 
 
@@ -293,7 +294,8 @@ def main():
     if rank == 0:
         # per-ray algorithmic work from the oracle's counters: one 1-spp pass of the same workload
         orc = oracle_scene_for(doc, cfg, assets)
-        _, _, cst = orc.render(cfg.renderer(width=width, height=height, samples=1, seed=1).params(), want_rgb=False)
+        _, _, cst = orc.render(cfg.renderer(width=width, height=height, samples=1, seed=1).params(), want_rgb=False,
+                               threads=len(os.sched_getaffinity(0)))
         flops_ray, bytes_ray, per_ray = per_ray_work(cst)
         ext_s = max(totals["ms_extend"], 1e-9) * 1e-3
         my_rays = totals["rays"]
