@@ -61,7 +61,10 @@ struct fw_scene {
     int device = 0;
     int sm_count = 148;
     int bvh_blocks_per_sm = 4;
-    int extend_mode = 0;     // 0 = grid-stride extend (default), 1 = persistent dynamic-fetch variant (measured slower; FW_EXTEND_MODE)
+    int extend_mode = 0;     // 0 = grid-stride extend on every bounce (default: measured fastest); 1 = persistent dynamic-fetch extend from bounce
+                             // `persistent_from_bounce` on (knobs: FW_EXTEND_MODE, FW_PERSISTENT_FROM, FW_REFILL_LANES)
+    int persistent_from_bounce = 1;
+    int two_pass = 1;        // two-pass extend for BVH scenes with top-level meshes (FW_TWO_PASS)
     int refill_lanes = FW_REFILL_LANES;
     DeviceScene dscene{};
     std::vector<void*> allocs;
@@ -91,7 +94,7 @@ static void destroy_ctx(RenderCtx* c) {
     cudaSetDevice(c->device);
     auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     fr(c->ps.ray_o); fr(c->ps.ray_d); fr(c->ps.win_a); fr(c->ps.win_b); fr(c->ps.atten);
-    fr(c->ps.radiance); fr(c->ps.q_extend[0]); fr(c->ps.q_extend[1]); fr(c->ps.counters);
+    fr(c->ps.radiance); fr(c->ps.q_extend[0]); fr(c->ps.q_extend[1]); fr(c->ps.q_mesh); fr(c->ps.counters);
     for (int k = 0; k < MAT_NUM_QUEUES; ++k) fr(c->ps.q_mat[k]);
     fr(c->d_sum); fr(c->d_rgb);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -288,7 +291,7 @@ int fw_scene_commit(fw_scene* sc, int device) {
     sc->sm_count = prop.multiProcessorCount;
     {
         int nb = 0;
-        FW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extend_bvh_kernel, 128, 0));
+        FW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extend_bvh_persistent_kernel<false, true>, 128, 0));
         sc->bvh_blocks_per_sm = std::max(nb, 1);
     }
     {
@@ -413,7 +416,7 @@ static int ensure_path_state(fw_scene* sc, size_t cap) {
     auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     PathState& ps = ctx->ps;
     fr(ps.ray_o); fr(ps.ray_d); fr(ps.win_a); fr(ps.win_b); fr(ps.atten); fr(ps.radiance);
-    fr(ps.q_extend[0]); fr(ps.q_extend[1]); fr(ps.counters);
+    fr(ps.q_extend[0]); fr(ps.q_extend[1]); fr(ps.q_mesh); fr(ps.counters);
     for (int k = 0; k < MAT_NUM_QUEUES; ++k) fr(ps.q_mat[k]);
     ctx->ps_cap = 0;
     FW_CUDA(cudaMalloc(&ps.ray_o, cap * sizeof(float4)));
@@ -424,6 +427,7 @@ static int ensure_path_state(fw_scene* sc, size_t cap) {
     FW_CUDA(cudaMalloc(&ps.radiance, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.q_extend[0], cap * sizeof(uint32_t)));
     FW_CUDA(cudaMalloc(&ps.q_extend[1], cap * sizeof(uint32_t)));
+    FW_CUDA(cudaMalloc(&ps.q_mesh, cap * sizeof(uint32_t)));
     for (int k = 0; k < MAT_NUM_QUEUES; ++k) FW_CUDA(cudaMalloc(&ps.q_mat[k], cap * sizeof(uint32_t)));
     FW_CUDA(cudaMalloc(&ps.counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_COUNTERS_PER_BOUNCE));
     ps.cap = (uint32_t)cap;
@@ -497,15 +501,31 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
             FW_CUDA(cudaMemcpy(&rd, ps.ray_d + worst, 16, cudaMemcpyDeviceToHost));
             fprintf(stderr, "[fw debug] bounce %u: box tests total %llu, worst path %zu (pixel %zu sample %zu): %u tests, o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g)\n",
                     bounce, sum, worst, (size_t)b.pix0 + worst % b.npix, (size_t)b.s0 + worst / b.npix, hs[worst], ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
-        } else if (use_bvh && sc->extend_mode == 0) {
+        } else if (use_bvh && sc->flat.has_top_mesh && sc->two_pass) {
+            if (sc->flat.has_medium_mesh) {
+                extend_pass1_kernel<true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+                extend_pass2_kernel<true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, row);
+            } else {
+                extend_pass1_kernel<false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+                extend_pass2_kernel<false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, row);
+            }
+            tot.launches++;
+        } else if (use_bvh && (sc->extend_mode == 0 || (int)bounce < sc->persistent_from_bounce)) {
             if (sc->flat.has_medium_mesh)
                 extend_bvh_simple_kernel<true, true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
-            else
+            else if (sc->flat.has_mesh)
                 extend_bvh_simple_kernel<false, true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
-        } else if (use_bvh && sc->extend_mode == 2) {
-            extend_bvh_simple_kernel<true, false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+            else
+                extend_bvh_simple_kernel<false, false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
         } else if (use_bvh) {
-            extend_bvh_kernel<<<g_bvh, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, sc->refill_lanes);
+            if (sc->flat.has_medium_mesh)
+                extend_bvh_persistent_kernel<true, true><<<g_bvh, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, sc->refill_lanes);
+            else if (sc->flat.has_mesh)
+                extend_bvh_persistent_kernel<false, true><<<g_bvh, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, sc->refill_lanes);
+            else
+                extend_bvh_persistent_kernel<false, false><<<g_bvh, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, sc->refill_lanes);
+            classify_kernel<<<g_sh, 256, 0, st>>>(S, ps, q_in, count_in, N, row);
+            tot.launches++;
         } else if (sc->flat.has_mesh) {
             extend_linear_kernel<true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
         } else {
@@ -568,6 +588,8 @@ static int render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStrea
     size_t cap = sc->batch_paths ? sc->batch_paths : ((size_t)1 << 22);
     if (const char* e = getenv("FW_BATCH_PATHS")) cap = std::max<size_t>(1024, strtoull(e, nullptr, 10));
     if (const char* e = getenv("FW_EXTEND_MODE")) sc->extend_mode = atoi(e);
+    if (const char* e = getenv("FW_TWO_PASS")) sc->two_pass = atoi(e);
+    if (const char* e = getenv("FW_PERSISTENT_FROM")) sc->persistent_from_bounce = atoi(e);
     if (const char* e = getenv("FW_REFILL_LANES")) sc->refill_lanes = std::max(1, std::min(32, atoi(e)));
     cap = std::min<size_t>(cap, npix * std::max<uint32_t>(p->sample_count, 1));
     cap = std::max<size_t>(cap, 32);

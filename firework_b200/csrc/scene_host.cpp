@@ -701,7 +701,7 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
             out.obj_irot.push_back(float4{Ri.c[c].x, Ri.c[c].y, Ri.c[c].z, 0});
         }
         if (s.kind == SH_MEDIUM) out.has_medium = true;
-        if (s.kind == SH_MESH) out.has_mesh = true;
+        if (s.kind == SH_MESH) out.has_mesh = out.has_top_mesh = true;
         if (s.kind == SH_MEDIUM && desc.shapes[s.i0].kind == SH_MESH) out.has_mesh = out.has_medium_mesh = true;
         obj_unbounded[i] = shape_unbounded(o.shape) ? 1 : 0;
     }

@@ -86,6 +86,7 @@ struct HostFlat {
     bool has_medium = false;
     int nan_bvh_obj = -1, nan_bvh_prim = 0, nan_lin_obj = -1, nan_lin_prim = 0;
     bool has_mesh = false;          // some object is (or wraps) a TriangleMesh
+    bool has_top_mesh = false;      // some render object IS a TriangleMesh
     bool has_medium_mesh = false;   // some ConstantMedium wraps a TriangleMesh
 };
 bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err);

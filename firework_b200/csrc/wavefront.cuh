@@ -23,6 +23,7 @@ struct PathState {
     float4* atten;     // [FW_MAX_DEPTH][cap] attenuation chain (see fold_radiance)
     float4* radiance;  // [cap] finished path radiance
     uint32_t* q_extend[2];             // ping-pong extend queues
+    uint32_t* q_mesh;                  // paths whose ray still has to walk a mesh (two-pass extend)
     uint32_t* q_mat[MAT_NUM_QUEUES];   // per-material shade queues
     uint32_t* counters;                // [FW_MAX_DEPTH + 2][FW_COUNTERS_PER_BOUNCE]
     uint32_t cap;
@@ -91,12 +92,6 @@ FW_DEV void warp_enqueue(uint32_t* const* queues, uint32_t* counters, int mine, 
 // extend: closest hit for every queued path; writes the winning (t, object, primitive, barycentrics) and
 // sorts the path into its material's shade queue (or the miss queue).  The full hit record is rebuilt by the
 // shade kernel that consumes it (finalize_hit), so it never travels through HBM.
-//
-// BVH scenes: persistent warps with dynamic ray fetch.  A lane whose ray has finished parks until the warp
-// reaches the converged top of the loop, where finished lanes publish their result (one ballot per material
-// queue) and free lanes pull new rays from the queue with one atomicAdd per warp.  While work remains the
-// traversal burst ends as soon as fewer than FW_REFILL_LANES lanes are still walking, so a few long rays do
-// not hold 31 idle lanes hostage.
 constexpr int FW_REFILL_LANES = 22;
 
 FW_DEV void store_winner(const PathState& ps, uint32_t path, const Winner& w) {
@@ -121,76 +116,90 @@ FW_DEV int winner_queue(const DeviceScene& S, const Winner& w) {
     return __ldg(&S.mats[winner_material(S, w.obj, w.h.prim)].kind);
 }
 
-__global__ void __launch_bounds__(128) extend_bvh_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
-                                                         const uint32_t* __restrict__ q_in,
-                                                         const uint32_t* __restrict__ count_in, uint32_t n_direct,
-                                                         uint32_t* counters_out, int refill_lanes) {
+// Persistent variant for incoherent bounces: each warp reserves FW_CHUNK_RAYS queue entries at a time (one
+// atomicAdd per chunk) and hands them to lanes as they free up; a finished lane just stores its winner record
+// (classification into material queues is a separate, fully converged pass: classify_kernel).  The traversal
+// burst ends when fewer than `refill_lanes` lanes are still walking, as long as there is work left to hand out.
+constexpr int FW_CHUNK_RAYS = 128;
+template <bool NESTED, bool MESHES>
+__global__ void __launch_bounds__(128) extend_bvh_persistent_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                                    const uint32_t* __restrict__ q_in,
+                                                                    const uint32_t* __restrict__ count_in, uint32_t n_direct,
+                                                                    uint32_t* counters_out, int refill_lanes) {
     const uint32_t total = count_in ? *count_in : n_direct;
     uint32_t* cursor = counters_out + 7;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt = (1u << lane) - 1u;
-    enum { EMPTY = 0, ACTIVE = 1, DONE = 2 };
-    int state = EMPTY;
+    bool active = false;
     uint32_t path = 0;
-    bool more = true;
+    uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
+    bool more = true;                        // warp-uniform: the global queue may still have entries
     RngKey key{seed, 0u, 0u, bounce};
-    float3 o = f3(0.0f, 0.0f, 0.0f), d = f3(0.0f, 0.0f, 1.0f);
-    BvhWalker<false> walker;
-    TopLeaf<false> leaf(S, o, d, key, nullptr);
+    UnifiedWalker<false, NESTED, MESHES> wk;
+    int stack_code[FW_STACK];
+    float stack_te[FW_STACK];
     for (;;) {
-        // ---- converged: publish finished rays
-        unsigned done = __ballot_sync(0xffffffffu, state == DONE);
-        if (done) {
-            int mine = -1;
-            if (state == DONE) {
-                store_winner(ps, path, leaf.w);
-                mine = winner_queue(S, leaf.w);
-                state = EMPTY;
+        unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle) {
+            if (chunk_next >= chunk_end && more) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, (uint32_t)FW_CHUNK_RAYS);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                chunk_next = base;
+                chunk_end = min(base + (uint32_t)FW_CHUNK_RAYS, total);
+                if (base >= total) { more = false; chunk_next = chunk_end = 0; }
             }
-            warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
-        }
-        // ---- converged: refill free lanes
-        unsigned empty = __ballot_sync(0xffffffffu, state == EMPTY);
-        if (empty && more) {
-            int n = __popc(empty);
-            int leader = __ffs(empty) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)n);
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (base + (uint32_t)n >= total) more = false;
-            if (state == EMPTY) {
-                uint32_t i = base + __popc(empty & lt);
-                if (i < total) {
+            if (chunk_next < chunk_end) {
+                uint32_t i = chunk_next + __popc(idle & lt);
+                if (!active && i < chunk_end) {
                     path = q_in ? q_in[i] : i;
-                    float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
-                    o = f3(ro); d = f3(rd);
+                    float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
                     batch_path(b, path, key.pixel, key.sample);
-                    leaf.o = o; leaf.d = d;
-                    leaf.w.found = false; leaf.w.t = 0.0f; leaf.w.obj = -1; leaf.w.rank = -1;
-                    leaf.bnd = FW_FLT_MAX;
-                    state = walker.init(S.nodes, 0, o, d, 0.001f, 2e9f, nullptr) ? ACTIVE : DONE;
+                    if (wk.init(S, o, d, stack_code, stack_te, nullptr)) active = true;
+                    else store_winner(ps, path, wk.w);
                 }
+                chunk_next = min(chunk_next + (uint32_t)__popc(idle), chunk_end);
             }
         }
-        unsigned active = __ballot_sync(0xffffffffu, state == ACTIVE);
-        if (active == 0u) {
-            if (__ballot_sync(0xffffffffu, state == DONE)) continue;
+        unsigned act = __ballot_sync(0xffffffffu, active);
+        bool can_refill = more || chunk_next < chunk_end;
+        if (act == 0u) {
+            if (can_refill) continue;
             break;
         }
-        // ---- traversal burst
-        int keep = more ? min(__popc(active), refill_lanes) : 1;
+        int keep = can_refill ? min(__popc(act), refill_lanes) : 1;
         do {
-            if (state == ACTIVE) {
-                if (!walker.step(S.nodes, leaf, nullptr)) state = DONE;
+            if (active) {
+                if (!wk.step(S, key, nullptr)) {
+                    store_winner(ps, path, wk.w);
+                    active = false;
+                }
             }
-        } while (__popc(__ballot_sync(0xffffffffu, state == ACTIVE)) >= keep);
+        } while (__popc(__ballot_sync(0xffffffffu, active)) >= keep);
     }
 }
 
-// BVH scenes: one ray per thread per grid-stride iteration, unified two-level traversal run to completion.
-// Consecutive lanes hold consecutive pixels (primary) / consecutive queue entries, which keeps warps coherent;
-// the persistent dynamic-fetch variant above was measured 10-30 % slower on every scene because refilling
-// mixes unrelated rays into a warp (profiles/r01_extend_variants.md).
+// Sorts the paths of an extend queue into the per-material shade queues from their winner records (used after
+// extend_bvh_persistent_kernel; the grid-stride extend kernels do this themselves).
+__global__ void __launch_bounds__(256) classify_kernel(DeviceScene S, PathState ps, const uint32_t* __restrict__ q_in,
+                                                       const uint32_t* __restrict__ count_in, uint32_t n_direct,
+                                                       uint32_t* counters_out) {
+    uint32_t total = count_in ? *count_in : n_direct;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        uint32_t i = base + threadIdx.x;
+        int mine = -1;
+        uint32_t path = 0;
+        if (i < total) {
+            path = q_in ? q_in[i] : i;
+            float4 a = ps.win_a[path];
+            int obj = __float_as_int(a.y);
+            mine = obj < 0 ? (int)MAT_MISS : __ldg(&S.mats[winner_material(S, obj, __float_as_int(a.z))].kind);
+        }
+        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
+    }
+}
+
 // Debug twin of the BVH extend: also records the number of box tests each path needed (FW_DEBUG_STEPS=1).
 __global__ void __launch_bounds__(128) extend_bvh_debug_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
                                                                const uint32_t* __restrict__ q_in,
@@ -218,7 +227,84 @@ __global__ void __launch_bounds__(128) extend_bvh_debug_kernel(DeviceScene S, Pa
     }
 }
 
-template <bool NESTED, bool UNIFIED>
+// Two-pass extend for BVH scenes with TriangleMesh objects (see UnifiedWalker PHASE).  Pass 1 settles every ray
+// against the non-mesh objects and the mesh root boxes; rays that must enter a mesh are compacted into q_mesh
+// (counter slot 7) and finished by pass 2, where every lane of a warp is doing real mesh traversal.
+template <bool NESTED>
+__global__ void __launch_bounds__(128) extend_pass1_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                           const uint32_t* __restrict__ q_in,
+                                                           const uint32_t* __restrict__ count_in, uint32_t n_direct,
+                                                           uint32_t* counters_out) {
+    uint32_t total = count_in ? *count_in : n_direct;
+    uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t* q7[MAT_NUM_QUEUES + 2];
+#pragma unroll
+    for (int k = 0; k < MAT_NUM_QUEUES; ++k) q7[k] = ps.q_mat[k];
+    q7[6] = nullptr;
+    q7[7] = ps.q_mesh;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        uint32_t i = base + threadIdx.x;
+        int mine = -1;
+        uint32_t path = 0;
+        if (i < total) {
+            path = q_in ? q_in[i] : i;
+            float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            UnifiedWalker<false, NESTED, true, 1> wk;
+            int stack_code[FW_STACK];
+            float stack_te[FW_STACK];
+            if (wk.init(S, o, d, stack_code, stack_te, nullptr)) {
+                while (wk.step(S, key, nullptr)) {
+                }
+            }
+            store_winner(ps, path, wk.w);
+            if (wk.pending) {
+                if (wk.w.found) ps.win_b[path] = make_float2(__int_as_float(wk.w.rank), 0.0f);  // pass 2 needs the rank
+                mine = 7;
+            } else {
+                mine = winner_queue(S, wk.w);
+            }
+        }
+        // queue 6 is never selected (slot 6 of the counter row belongs to the shade kernels)
+        warp_enqueue<MAT_NUM_QUEUES + 2>(q7, counters_out, mine, path);
+    }
+}
+template <bool NESTED>
+__global__ void __launch_bounds__(128) extend_pass2_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                           uint32_t* counters_out) {
+    uint32_t total = counters_out[7];
+    const uint32_t* __restrict__ q_in = ps.q_mesh;
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        uint32_t i = base + threadIdx.x;
+        int mine = -1;
+        uint32_t path = 0;
+        if (i < total) {
+            path = q_in[i];
+            float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            UnifiedWalker<false, NESTED, true, 2> wk;
+            float4 a = ps.win_a[path];
+            wk.w.found = __float_as_int(a.y) >= 0;
+            wk.w.t = a.x; wk.w.obj = __float_as_int(a.y); wk.w.rank = -1;
+            wk.w.h.t = a.x; wk.w.h.prim = __float_as_int(a.z); wk.w.h.b0 = a.w; wk.w.h.b1 = wk.w.h.b2 = 0.0f;
+            if (wk.w.found) wk.w.rank = __float_as_int(ps.win_b[path].x);
+            int stack_code[FW_STACK];
+            float stack_te[FW_STACK];
+            if (wk.init(S, o, d, stack_code, stack_te, nullptr)) {
+                while (wk.step(S, key, nullptr)) {
+                }
+            }
+            store_winner(ps, path, wk.w);
+            mine = winner_queue(S, wk.w);
+        }
+        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
+    }
+}
+
+template <bool NESTED, bool MESHES>
 __global__ void __launch_bounds__(128) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
                                                                 const uint32_t* __restrict__ q_in,
                                                                 const uint32_t* __restrict__ count_in, uint32_t n_direct,
@@ -236,13 +322,7 @@ __global__ void __launch_bounds__(128) extend_bvh_simple_kernel(DeviceScene S, P
             RngKey key{seed, 0u, 0u, bounce};
             batch_path(b, path, key.pixel, key.sample);
             Winner w;
-            if (UNIFIED) {
-                trace_unified<false, NESTED>(S, o, d, key, w, nullptr);
-            } else {
-                TopLeaf<false> leaf(S, o, d, key, nullptr);
-                bvh_traverse<TopLeaf<false>, false>(S.nodes, 0, o, d, 0.001f, 2e9f, leaf, nullptr);
-                w = leaf.w;
-            }
+            trace_unified<false, NESTED, MESHES>(S, o, d, key, w, nullptr);
             store_winner(ps, path, w);
             mine = winner_queue(S, w);
         }
