@@ -31,7 +31,7 @@ static int set_error(int code, const std::string& msg) {
     } while (0)
 
 static_assert(sizeof(fw_params) == sizeof(RenderParamsHost), "fw_params layout");
-static_assert(sizeof(ShapeRec) == 48 && sizeof(MeshRec) == 32 && sizeof(MatRec) == 32 && sizeof(TexRec) == 32, "rec sizes");
+static_assert(sizeof(ShapeRec) == 48 && sizeof(MeshRec) == 64 && sizeof(MatRec) == 32 && sizeof(TexRec) == 32, "rec sizes");
 
 // Render-time device state (path-state streams, sum / image buffers, stream, events).  It is independent of the
 // scene, ~1.2 GB at the default batch size, and expensive to allocate, so contexts are cached per device and
@@ -328,9 +328,17 @@ int fw_scene_commit(fw_scene* sc, int device) {
     }
     if ((rc = upload(sc, images, &D.images)) != FW_OK) return rc;
     D.n_objects = (int)sc->desc.objects.size();
-    D.n_nodes = (int)(F.nodes.size() / 2);
+    D.n_nodes = (int)(F.nodes.size() / 8);
+    {
+        int rc_bits = F.top_root_code;
+        float rcf;
+        memcpy(&rcf, &rc_bits, 4);
+        D.top_lo = make_float4(F.top_root_box.mn.x, F.top_root_box.mn.y, F.top_root_box.mn.z, rcf);
+        D.top_hi = make_float4(F.top_root_box.mx.x, F.top_root_box.mx.y, F.top_root_box.mx.z, 0.0f);
+    }
     D.top_root_is_valid = 1;
     D.has_medium = F.has_medium ? 1 : 0;
+    D.has_unbounded = F.has_unbounded ? 1 : 0;
     D.nan_bvh_obj = F.nan_bvh_obj; D.nan_bvh_prim = F.nan_bvh_prim;
     D.nan_lin_obj = F.nan_lin_obj; D.nan_lin_prim = F.nan_lin_prim;
     for (const MatRec& m : F.mats) sc->mat_present[m.kind] = true;
@@ -340,7 +348,7 @@ int fw_scene_commit(fw_scene* sc, int device) {
 
 uint64_t fw_scene_device_bytes(const fw_scene* sc) { return sc ? sc->h2d_bytes : 0; }
 int fw_scene_num_objects(const fw_scene* sc) { return sc ? (int)sc->desc.objects.size() : 0; }
-int fw_scene_num_nodes(const fw_scene* sc) { return sc && sc->built ? (int)(sc->flat.nodes.size() / 2) : 0; }
+int fw_scene_num_nodes(const fw_scene* sc) { return sc && sc->built ? (int)(sc->flat.nodes.size() / 8) : 0; }
 int fw_scene_top_leaf_order(const fw_scene* sc, int* out, int cap) {
     if (!sc || !sc->built) return set_error(FW_ERR_STATE, "scene not built (fw_scene_build_host / fw_scene_commit)");
     int n = (int)sc->flat.top_items.size();

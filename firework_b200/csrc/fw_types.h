@@ -40,13 +40,14 @@ struct ShapeRec {  // 48 B
     int kind, material, i0, i1;
     float f[8];
 };
-struct MeshRec {  // 32 B
-    int node_root;   // index into nodes[] of this mesh's BVH root
+struct MeshRec {  // 64 B
+    int root_code;   // wide node index (>= 0) or leaf code (< 0) of this mesh's BVH root
     int tri_first;   // first triangle slot (triangles are stored in BVH leaf order)
     int tri_count;
     int flags;       // bit0 has_normals, bit1 has_uvs
     int material;
     int pad[3];
+    float lo[4], hi[4];  // the root's box (bvh.rs:117 tests it first)
 };
 struct MatRec {  // 32 B
     int kind, tex;
@@ -72,13 +73,16 @@ struct EnvRec {
     cudaTextureObject_t tex;  // HdrEnvironment: float4 point-sampled
 };
 
-// BVH node = 2 x float4:  lo = (min.xyz, asfloat(code)),  hi = (max.xyz, asfloat(flags))
-//   flags bit 0 : some item below has a box that does not bound its geometry (Disk) -> never distance-cull
-//   code >= 0 : interior, children at nodes code and code+1 (siblings adjacent, 64-byte aligned pair)
-//   code <  0 : leaf; p = ~code, items [p >> 1, (p >> 1) + (p & 1) + 1) of the tree's item list
-//               (1 or 2 items: bvh.rs Leaf / DoubleLeaf)
+// BVH: the reference's binary median-split tree (bvh.rs:21-71), collapsed two levels at a time into 4-wide nodes.
+// Wide node = 8 x float4 (128 B, one cache line):
+//   [0..2] child min x / y / z (one lane per child)   [3..5] child max x / y / z
+//   [6]    child codes (int bits):  >= 0 wide node index;  < 0 leaf: p = ~code, items [p >> 1, (p >> 1) + (p & 1) + 1)
+//          of the tree's item list (1 or 2 items: bvh.rs Leaf / DoubleLeaf); empty slots carry an inverted box
+//   [7]    child flags (int bits): bit 0 = some item below has a box that does not bound its geometry (Disk)
+//          -> that child is never distance-culled
 struct DeviceScene {
-    const float4* nodes;       // all trees; top-level root at node 0
+    const float4* nodes;       // wide nodes of all trees (top-level tree first)
+    float4 top_lo, top_hi;     // the top-level root's box; top_lo.w = asfloat(root code)
     const int* top_items;      // object ids in top-level DFS leaf order (rank = tie-break key, bvh.rs:128,141)
     const float4* leaf_posr;   // obj_posr reordered by top-level DFS leaf rank (no indirection in the leaf loop)
     const int4* leaf_meta;     // obj_meta reordered by rank; .w = object id
@@ -99,6 +103,7 @@ struct DeviceScene {
     int n_nodes;
     int top_root_is_valid;     // 0 if the top-level BVH was not built (linear scenes may still build it)
     int has_medium;
+    int has_unbounded;         // some top-level item's box does not bound its geometry (Disk): node flags matter
     // Closest-hit answer for a ray whose direction is NaN in all three components (see nan_direction_winner):
     // object id (-1 = miss) and primitive (mesh: last triangle slot, Rect3d: last face), for BVH and linear roots.
     int nan_bvh_obj, nan_bvh_prim, nan_lin_obj, nan_lin_prim;

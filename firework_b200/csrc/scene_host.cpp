@@ -457,34 +457,66 @@ bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& er
         return false;
     }
     out.items = b.order;
-    // Breadth-first layout: root at 0, node 1 is padding, sibling pairs at even indices.
-    out.nodes.assign(4, float4{0, 0, 0, 0});
-    std::deque<std::pair<int, int>> q;  // (build node, flat index)
-    q.emplace_back(root, 0);
-    int next = 2;
-    while (!q.empty()) {
-        auto [bn, fi] = q.front();
-        q.pop_front();
-        const BuildNode& n = b.nodes[bn];
-        out.max_depth = std::max(out.max_depth, n.depth);
-        int a, bb;
-        if (n.count > 0) {
-            a = ~(n.first * 2 + (n.count - 1));  // leaf code: items [first, first + count), count in {1, 2}
-            bb = n.unbounded ? 1 : 0;
-        } else {
-            a = next;
-            bb = n.unbounded ? 1 : 0;
-            next += 2;
-            if ((int)out.nodes.size() < 2 * next) out.nodes.resize(2 * (size_t)next, float4{0, 0, 0, 0});
-            q.emplace_back(n.left, a);
-            q.emplace_back(n.right, a + 1);
-        }
-        out.nodes[2 * fi] = float4{n.box.mn.x, n.box.mn.y, n.box.mn.z, as_float(a)};
-        out.nodes[2 * fi + 1] = float4{n.box.mx.x, n.box.mx.y, n.box.mx.z, as_float(bb)};
+    for (const BuildNode& n : b.nodes) out.max_depth = std::max(out.max_depth, n.depth);
+    // Collapse the reference's binary tree two levels at a time into 4-wide nodes (breadth-first, so the top
+    // levels are contiguous).  A wide node holds the boxes of the binary node's grandchildren (or of a child that
+    // is itself a leaf).  Skipping the intermediate child's box test cannot change which leaves are reached: the
+    // child's box contains the grandchild's, and the slab arithmetic (aabb.rs:38-47) is monotonic in the box
+    // planes, so "grandchild box hit" implies "child box hit" bit for bit.
+    auto leaf_code = [](const BuildNode& n) { return ~(n.first * 2 + (n.count - 1)); };  // items [first, first+count)
+    const BuildNode& rootn = b.nodes[root];
+    out.root_box = rootn.box;
+    if (rootn.count > 0) {
+        out.root_code = leaf_code(rootn);
+        return true;
     }
-    // padding node 1: an empty leaf with an inverted box (never reachable, never hit)
-    out.nodes[2] = float4{INFINITY, INFINITY, INFINITY, as_float(~0)};
-    out.nodes[3] = float4{-INFINITY, -INFINITY, -INFINITY, as_float(0)};
+    out.root_code = 0;
+    struct Pending { int bn; int wide; int depth; };
+    std::deque<Pending> q;
+    q.push_back(Pending{root, 0, 1});
+    int next_wide = 1;
+    out.nodes.assign(8, float4{0, 0, 0, 0});
+    while (!q.empty()) {
+        Pending cur = q.front();
+        q.pop_front();
+        out.wide_depth = std::max(out.wide_depth, cur.depth);
+        const BuildNode& n = b.nodes[cur.bn];
+        int kids[4], nk = 0;
+        for (int side : {n.left, n.right}) {
+            const BuildNode& c = b.nodes[side];
+            if (c.count > 0) kids[nk++] = side;
+            else { kids[nk++] = c.left; kids[nk++] = c.right; }
+        }
+        float lo[3][4], hi[3][4];
+        int code[4], flag[4];
+        for (int k = 0; k < 4; ++k) {
+            if (k < nk) {
+                const BuildNode& c = b.nodes[kids[k]];
+                lo[0][k] = c.box.mn.x; lo[1][k] = c.box.mn.y; lo[2][k] = c.box.mn.z;
+                hi[0][k] = c.box.mx.x; hi[1][k] = c.box.mx.y; hi[2][k] = c.box.mx.z;
+                flag[k] = c.unbounded ? 1 : 0;
+                if (c.count > 0) {
+                    code[k] = leaf_code(c);
+                } else {
+                    code[k] = next_wide;
+                    q.push_back(Pending{kids[k], next_wide, cur.depth + 1});
+                    ++next_wide;
+                    out.nodes.resize(8 * (size_t)next_wide, float4{0, 0, 0, 0});
+                }
+            } else {  // empty slot: an inverted box fails every slab test
+                for (int a = 0; a < 3; ++a) { lo[a][k] = INFINITY; hi[a][k] = -INFINITY; }
+                code[k] = (int)0x80000000;
+                flag[k] = 0;
+            }
+        }
+        float4* w = &out.nodes[8 * (size_t)cur.wide];
+        for (int a = 0; a < 3; ++a) {
+            w[a] = float4{lo[a][0], lo[a][1], lo[a][2], lo[a][3]};
+            w[3 + a] = float4{hi[a][0], hi[a][1], hi[a][2], hi[a][3]};
+        }
+        w[6] = float4{as_float(code[0]), as_float(code[1]), as_float(code[2]), as_float(code[3])};
+        w[7] = float4{as_float(flag[0]), as_float(flag[1]), as_float(flag[2]), as_float(flag[3])};
+    }
     return true;
 }
 
@@ -549,6 +581,7 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
     // Top-level tree occupies the front of nodes[]; it is appended after its size is known, so build
     // meshes into a side buffer first.
     std::vector<float4> mesh_nodes;
+    int max_mesh_wide_depth = 0;
     std::vector<Box> mesh_root_box(desc.meshes.size());
     std::vector<int> mesh_node_root(desc.meshes.size());
     for (size_t mi = 0; mi < desc.meshes.size(); ++mi) {
@@ -559,23 +592,20 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
             tb[t] = triangle_box(m.verts[m.indicies[3 * t]], m.verts[m.indicies[3 * t + 1]], m.verts[m.indicies[3 * t + 2]]);
         FlatBVH bvh;
         if (!build_bvh(tb, bvh, err)) return false;
-        if (bvh.max_depth >= 30) {
-            err = "mesh BVH deeper than the traversal stack";
-            return false;
-        }
+        max_mesh_wide_depth = std::max(max_mesh_wide_depth, bvh.wide_depth);
         MeshRec rec;
         memset(&rec, 0, sizeof(rec));
-        rec.node_root = (int)(mesh_nodes.size() / 2);  // relative; rebased below
+        rec.root_code = bvh.root_code;  // tree-local; rebased below
         rec.tri_first = (int)(out.tri_verts.size() / 3);
         rec.tri_count = (int)ntri;
         rec.flags = (m.has_normals ? 1 : 0) | (m.has_uvs ? 2 : 0);
         rec.material = m.material;
-        mesh_node_root[mi] = rec.node_root;
-        // nodes: child indices are tree-local; rebase interior links later (after top-level size is known)
+        mesh_node_root[mi] = (int)(mesh_nodes.size() / 8);
+        // child links are tree-local; rebased after the top-level tree's size is known
         mesh_nodes.insert(mesh_nodes.end(), bvh.nodes.begin(), bvh.nodes.end());
-        const float4& rlo = bvh.nodes[0];
-        const float4& rhi = bvh.nodes[1];
-        mesh_root_box[mi] = Box{V3{rlo.x, rlo.y, rlo.z}, V3{rhi.x, rhi.y, rhi.z}};
+        mesh_root_box[mi] = bvh.root_box;
+        rec.lo[0] = bvh.root_box.mn.x; rec.lo[1] = bvh.root_box.mn.y; rec.lo[2] = bvh.root_box.mn.z; rec.lo[3] = 0;
+        rec.hi[0] = bvh.root_box.mx.x; rec.hi[1] = bvh.root_box.mx.y; rec.hi[2] = bvh.root_box.mx.z; rec.hi[3] = 0;
         for (size_t slot = 0; slot < ntri; ++slot) {
             int t = bvh.items[slot];
             uint32_t i0 = m.indicies[3 * t], i1 = m.indicies[3 * t + 1], i2 = m.indicies[3 * t + 2];
@@ -704,13 +734,15 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         if (s.kind == SH_MESH) out.has_mesh = out.has_top_mesh = true;
         if (s.kind == SH_MEDIUM && desc.shapes[s.i0].kind == SH_MESH) out.has_mesh = out.has_medium_mesh = true;
         obj_unbounded[i] = shape_unbounded(o.shape) ? 1 : 0;
+        if (obj_unbounded[i]) out.has_unbounded = true;
     }
 
     // top-level BVH (bvh.rs:79-98), always built: linear-scan renders simply do not use it
     FlatBVH top;
     if (!build_bvh(out.obj_aabb, top, err, &obj_unbounded)) return false;
-    if (top.max_depth >= 30) {
-        err = "top-level BVH deeper than the traversal stack";
+    // traversal stack: up to 3 deferred siblings per wide level, on both levels, plus EXIT / ENTER markers
+    if (3 * (top.wide_depth + max_mesh_wide_depth) + 8 > 64) {
+        err = "BVH deeper than the traversal stack";
         return false;
     }
     out.top_items = top.items;
@@ -721,12 +753,10 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         out.leaf_meta.push_back(m);
     }
     out.top_depth = top.max_depth;
-    out.top_nodes = (int)(top.nodes.size() / 2);
+    out.top_nodes = (int)(top.nodes.size() / 8);
     out.nodes = top.nodes;
-    if ((out.nodes.size() / 2) % 2) {  // keep every tree's root on an even node index
-        out.nodes.push_back(float4{INFINITY, INFINITY, INFINITY, as_float(~0)});
-        out.nodes.push_back(float4{-INFINITY, -INFINITY, -INFINITY, as_float(0)});
-    }
+    out.top_root_box = top.root_box;
+    out.top_root_code = top.root_code;
     // A ray with an all-NaN direction (e.g. after scattering off a zero-length interpolated normal) passes every
     // slab test (f32::max/min ignore NaN, aabb.rs:46-48) and is then "hit" by every primitive whose rejection
     // tests are all comparisons (NaN compares false): AARect (rect.rs:51,55), Triangle (mesh.rs:170-186), Disk,
@@ -754,26 +784,26 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
             if (accepts(obj, prim)) { out.nan_lin_obj = obj; out.nan_lin_prim = prim; break; }
         }
     }
-    int base = (int)(out.nodes.size() / 2);
-    // append mesh trees, rebasing interior child links and mesh roots
+    // append the mesh trees, rebasing child links and roots
+    int base = (int)(out.nodes.size() / 8);
     size_t start = out.nodes.size();
     out.nodes.insert(out.nodes.end(), mesh_nodes.begin(), mesh_nodes.end());
-    {
-        // each mesh tree's links are local to that tree: rebase by (base + tree offset)
-        for (size_t mi = 0; mi < out.meshes.size(); ++mi) {
-            int tree_off = mesh_node_root[mi];
-            int tree_end = (mi + 1 < out.meshes.size()) ? mesh_node_root[mi + 1] : (int)(mesh_nodes.size() / 2);
-            for (int n = tree_off; n < tree_end; ++n) {
-                float4& lo = out.nodes[start + 2 * (size_t)n];
+    for (size_t mi = 0; mi < out.meshes.size(); ++mi) {
+        int tree_off = mesh_node_root[mi];
+        int tree_end = (mi + 1 < out.meshes.size()) ? mesh_node_root[mi + 1] : (int)(mesh_nodes.size() / 8);
+        for (int n = tree_off; n < tree_end; ++n) {
+            float4& codes = out.nodes[start + 8 * (size_t)n + 6];
+            float* cf = &codes.x;
+            for (int k = 0; k < 4; ++k) {
                 int a;
-                memcpy(&a, &lo.w, 4);
+                memcpy(&a, &cf[k], 4);
                 if (a >= 0) {
                     a += base + tree_off;
-                    lo.w = as_float(a);
+                    cf[k] = as_float(a);
                 }
             }
-            out.meshes[mi].node_root = base + tree_off;
         }
+        if (out.meshes[mi].root_code >= 0) out.meshes[mi].root_code += base + tree_off;
     }
     return true;
 }

@@ -58,9 +58,12 @@ bool load_scene_yaml(const char* text, size_t len, SceneDesc& out, std::string& 
 
 // One BVH in flattened form (see fw_types.h for the node encoding).
 struct FlatBVH {
-    std::vector<float4> nodes;   // 2 per node, indices local to this tree (root = node 0, node 1 = padding)
+    std::vector<float4> nodes;   // 8 float4 per WIDE node (fw_types.h), child links local to this tree
     std::vector<int> items;      // item ids in DFS leaf order
-    int max_depth = 0;
+    Box root_box{};              // the binary root's box (bvh.rs:117 tests it before anything else)
+    int root_code = 0;           // wide node index (>= 0) or leaf code (< 0) of the root
+    int max_depth = 0;           // depth of the reference's binary tree
+    int wide_depth = 0;          // depth of the collapsed 4-wide tree
 };
 // The reference's median split (bvh.rs:21-71): stable sort on centroid[depth % 3], leaves of 1 or 2.
 // `item_unbounded` (optional, same length as item_boxes) marks items whose box does NOT bound their geometry
@@ -83,7 +86,10 @@ struct HostFlat {
     std::vector<TexRec> texs;
     int top_depth = 0;
     int top_nodes = 0;
+    Box top_root_box{};
+    int top_root_code = 0;
     bool has_medium = false;
+    bool has_unbounded = false;
     int nan_bvh_obj = -1, nan_bvh_prim = 0, nan_lin_obj = -1, nan_lin_prim = 0;
     bool has_mesh = false;          // some object is (or wraps) a TriangleMesh
     bool has_top_mesh = false;      // some render object IS a TriangleMesh
