@@ -430,7 +430,7 @@ static int ensure_path_state(fw_scene* sc, size_t cap) {
     FW_CUDA(cudaMalloc(&ps.ray_o, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.ray_d, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.win_a, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.win_b, cap * sizeof(float2)));
+    FW_CUDA(cudaMalloc(&ps.win_b, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.atten, cap * sizeof(float4) * FW_MAX_DEPTH));
     FW_CUDA(cudaMalloc(&ps.radiance, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.q_extend[0], cap * sizeof(uint32_t)));

@@ -18,8 +18,8 @@ constexpr int FW_COUNTERS_PER_BOUNCE = 8; // [0..5] material queues (MatKind), [
 struct PathState {
     float4* ray_o;     // [cap] origin.xyz
     float4* ray_d;     // [cap] direction.xyz (never normalised: ray.rs)
-    float4* win_a;     // [cap] winning hit: t, asfloat(object), asfloat(primitive), b0
-    float2* win_b;     // [cap] b1, b2 (triangle barycentrics)
+    float4* win_a;     // [cap] winning hit: t, asfloat(object), asfloat(primitive), asfloat(material)  (object -1 = miss)
+    float4* win_b;     // [cap] triangle barycentrics b0, b1, b2 (written for mesh hits only); .w = rank between passes
     float4* atten;     // [FW_MAX_DEPTH][cap] attenuation chain (see fold_radiance)
     float4* radiance;  // [cap] finished path radiance
     uint32_t* q_extend[2];             // ping-pong extend queues
@@ -94,26 +94,37 @@ FW_DEV void warp_enqueue(uint32_t* const* queues, uint32_t* counters, int mine, 
 // shade kernel that consumes it (finalize_hit), so it never travels through HBM.
 constexpr int FW_REFILL_LANES = 22;
 
-FW_DEV void store_winner(const PathState& ps, uint32_t path, const Winner& w) {
-    if (w.found) {
-        ps.win_a[path] = make_float4(w.t, __int_as_float(w.obj), __int_as_float(w.h.prim), w.h.b0);
-        ps.win_b[path] = make_float2(w.h.b1, w.h.b2);
-    } else {
-        ps.win_a[path] = make_float4(0.0f, __int_as_float(-1), 0.0f, 0.0f);
+// Publishes a ray's result and returns the shade queue it belongs to.  The material index travels with the
+// record so that the shade kernel can fetch its material in parallel with the object records.
+FW_DEV int store_winner(const DeviceScene& S, const PathState& ps, uint32_t path, const Winner& w) {
+    if (!w.found) {
+        ps.win_a[path] = make_float4(0.0f, __int_as_float(-1), 0.0f, __int_as_float(-1));
+        return MAT_MISS;
     }
+    int4 meta = __ldg(&S.obj_meta[w.obj]);
+    int kind = meta.x & OBJ_KIND_MASK;
+    int material = meta.y;
+    if (kind == SH_RECT3D) material = winner_material(S, w.obj, w.h.prim);  // faces may carry their own material
+    ps.win_a[path] = make_float4(w.t, __int_as_float(w.obj), __int_as_float(w.h.prim), __int_as_float(material));
+    if (kind == SH_MESH) ps.win_b[path] = make_float4(w.h.b0, w.h.b1, w.h.b2, 0.0f);
+    return __ldg(&S.mats[material].kind);
 }
-FW_DEV Winner load_winner(const PathState& ps, uint32_t path) {
+FW_DEV Winner load_winner(const PathState& ps, uint32_t path, int& material) {
     float4 a = ps.win_a[path];
-    float2 b = ps.win_b[path];
     Winner w;
     w.found = true;
     w.t = a.x; w.obj = __float_as_int(a.y); w.rank = 0;
-    w.h.t = a.x; w.h.prim = __float_as_int(a.z); w.h.b0 = a.w; w.h.b1 = b.x; w.h.b2 = b.y;
+    w.h.t = a.x; w.h.prim = __float_as_int(a.z);
+    material = __float_as_int(a.w);
+    w.h.b0 = w.h.b1 = w.h.b2 = 0.0f;
     return w;
 }
-FW_DEV int winner_queue(const DeviceScene& S, const Winner& w) {
-    if (!w.found) return MAT_MISS;
-    return __ldg(&S.mats[winner_material(S, w.obj, w.h.prim)].kind);
+// Barycentrics are only stored (and only needed) for TriangleMesh hits.
+FW_DEV void load_winner_bary(const DeviceScene& S, const PathState& ps, uint32_t path, Winner& w) {
+    if ((__ldg(&S.obj_meta[w.obj]).x & OBJ_KIND_MASK) == SH_MESH) {
+        float4 b = ps.win_b[path];
+        w.h.b0 = b.x; w.h.b1 = b.y; w.h.b2 = b.z;
+    }
 }
 
 // Persistent variant for incoherent bounces: each warp reserves FW_CHUNK_RAYS queue entries at a time (one
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(128) extend_bvh_persistent_kernel(DeviceScene 
                     float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
                     batch_path(b, path, key.pixel, key.sample);
                     if (wk.init(S, o, d, stack_code, stack_te, nullptr)) active = true;
-                    else store_winner(ps, path, wk.w);
+                    else store_winner(S, ps, path, wk.w);
                 }
                 chunk_next = min(chunk_next + (uint32_t)__popc(idle), chunk_end);
             }
@@ -171,7 +182,7 @@ __global__ void __launch_bounds__(128) extend_bvh_persistent_kernel(DeviceScene 
         do {
             if (active) {
                 if (!wk.step(S, key, nullptr)) {
-                    store_winner(ps, path, wk.w);
+                    store_winner(S, ps, path, wk.w);
                     active = false;
                 }
             }
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(256) classify_kernel(DeviceScene S, PathState 
             path = q_in ? q_in[i] : i;
             float4 a = ps.win_a[path];
             int obj = __float_as_int(a.y);
-            mine = obj < 0 ? (int)MAT_MISS : __ldg(&S.mats[winner_material(S, obj, __float_as_int(a.z))].kind);
+            mine = obj < 0 ? (int)MAT_MISS : __ldg(&S.mats[__float_as_int(a.w)].kind);
         }
         warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
     }
@@ -220,8 +231,7 @@ __global__ void __launch_bounds__(128) extend_bvh_debug_kernel(DeviceScene S, Pa
             Counters cnt{0, 0};
             trace_unified<true, true>(S, o, d, key, w, &cnt);
             steps[path] = (uint32_t)cnt.node_tests;
-            store_winner(ps, path, w);
-            mine = winner_queue(S, w);
+            mine = store_winner(S, ps, path, w);
         }
         warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
     }
@@ -258,12 +268,11 @@ __global__ void __launch_bounds__(128) extend_pass1_kernel(DeviceScene S, PathSt
                 while (wk.step(S, key, nullptr)) {
                 }
             }
-            store_winner(ps, path, wk.w);
+            mine = store_winner(S, ps, path, wk.w);
             if (wk.pending) {
-                if (wk.w.found) ps.win_b[path] = make_float2(__int_as_float(wk.w.rank), 0.0f);  // pass 2 needs the rank
+                // pass 2 needs the rank of the pass-1 winner (a non-mesh object, so win_b is free)
+                if (wk.w.found) ps.win_b[path] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(wk.w.rank));
                 mine = 7;
-            } else {
-                mine = winner_queue(S, wk.w);
             }
         }
         // queue 6 is never selected (slot 6 of the counter row belongs to the shade kernels)
@@ -289,16 +298,15 @@ __global__ void __launch_bounds__(128) extend_pass2_kernel(DeviceScene S, PathSt
             float4 a = ps.win_a[path];
             wk.w.found = __float_as_int(a.y) >= 0;
             wk.w.t = a.x; wk.w.obj = __float_as_int(a.y); wk.w.rank = -1;
-            wk.w.h.t = a.x; wk.w.h.prim = __float_as_int(a.z); wk.w.h.b0 = a.w; wk.w.h.b1 = wk.w.h.b2 = 0.0f;
-            if (wk.w.found) wk.w.rank = __float_as_int(ps.win_b[path].x);
+            wk.w.h.t = a.x; wk.w.h.prim = __float_as_int(a.z); wk.w.h.b0 = wk.w.h.b1 = wk.w.h.b2 = 0.0f;
+            if (wk.w.found) wk.w.rank = __float_as_int(ps.win_b[path].w);
             int stack_code[FW_STACK];
             float stack_te[FW_STACK];
             if (wk.init(S, o, d, stack_code, stack_te, nullptr)) {
                 while (wk.step(S, key, nullptr)) {
                 }
             }
-            store_winner(ps, path, wk.w);
-            mine = winner_queue(S, wk.w);
+            mine = store_winner(S, ps, path, wk.w);
         }
         warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
     }
@@ -323,8 +331,7 @@ __global__ void __launch_bounds__(128) extend_bvh_simple_kernel(DeviceScene S, P
             batch_path(b, path, key.pixel, key.sample);
             Winner w;
             trace_unified<false, NESTED, MESHES>(S, o, d, key, w, nullptr);
-            store_winner(ps, path, w);
-            mine = winner_queue(S, w);
+            mine = store_winner(S, ps, path, w);
         }
         warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
     }
@@ -362,8 +369,7 @@ __global__ void __launch_bounds__(128) extend_linear_kernel(DeviceScene S, PathS
                     w.found = true; w.t = h.t; w.obj = obj; w.rank = obj; w.h = h;
                 }
             }
-            store_winner(ps, path, w);
-            mine = winner_queue(S, w);
+            mine = store_winner(S, ps, path, w);
         }
         warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
     }
@@ -401,10 +407,12 @@ __global__ void __launch_bounds__(256) shade_emissive_kernel(DeviceScene S, Path
     const uint32_t* q = ps.q_mat[MAT_EMISSIVE];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         uint32_t path = q[i];
-        Winner w = load_winner(ps, path);
+        int material;
+        Winner w = load_winner(ps, path, material);
+        load_winner_bary(S, ps, path, w);
         HitRecord rec;
         finalize_hit(S, w, f3(ps.ray_o[path]), f3(ps.ray_d[path]), rec, true);
-        int tex = __ldg(&S.mats[rec.material].tex);
+        int tex = __ldg(&S.mats[material].tex);
         float3 emit = texture_sample(S, tex, rec.uv, rec.point);
         float3 c = fold_radiance(ps, path, bounce, emit);
         ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
@@ -427,10 +435,11 @@ __global__ void __launch_bounds__(256) shade_scatter_kernel(DeviceScene S, PathS
         if (i < total) {
             path = q[i];
             float3 in_o = f3(ps.ray_o[path]), in_d = f3(ps.ray_d[path]);
-            Winner w = load_winner(ps, path);
-            int material = winner_material(S, w.obj, w.h.prim);
+            int material;
+            Winner w = load_winner(ps, path, material);
             const float4* mq = reinterpret_cast<const float4*>(&S.mats[material]);
             float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);  // (kind, tex, param, needs_uv), (albedo, -)
+            load_winner_bary(S, ps, path, w);
             HitRecord rec;
             finalize_hit(S, w, in_o, in_d, rec, __float_as_int(m0.w) != 0);
             float3 point = rec.point, normal = rec.normal;
