@@ -470,6 +470,15 @@ __global__ void __launch_bounds__(256) shade_scatter_kernel(DeviceScene S, PathS
     }
 }
 
+// Ray statistics without a host round trip per batch: rays traced = paths generated + every re-queued path.
+__global__ void tally_kernel(const uint32_t* __restrict__ counters, uint32_t n_paths, unsigned long long* total_rays) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long r = n_paths;
+        for (int bn = 0; bn < FW_MAX_DEPTH; ++bn) r += counters[bn * FW_COUNTERS_PER_BOUNCE + 6];
+        *total_rays += r;
+    }
+}
+
 // render.rs:177-182 `total_color += color(...)`: samples of a pixel are added in sample order, so the fp32
 // sum is independent of queue order and identical for any batch split along the sample axis.
 __global__ void __launch_bounds__(256) accumulate_kernel(float* __restrict__ sum, PathState ps, Batch b) {
