@@ -1,0 +1,159 @@
+"""GPU edge cases: degenerate trees (1 / 2 objects, 1-triangle mesh), ragged sizes, nested shapes, per-face
+materials, single samples — each compared with the oracle through the same gates as test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from firework_b200.api import (CameraSettings, CheckerTexture, ConstantTexture, Cone, Cylinder, DielectricMat, Disk,
+                               EmissiveMat, LambertianMat, MarbleTexture, MetalMat, PerlinNoiseTexture, Rect3d,
+                               RenderObject, Renderer, Rotor3, Scene, SkyEnv, Sphere, TriangleMesh, Vec3, XYRect,
+                               XZRect, YZRect)
+from firework_b200.engine import NativeScene
+from oracle.oracle import OracleScene
+
+pytestmark = pytest.mark.gpu
+
+
+def _renderer(w, h, spp, use_bvh, cam=(3.0, 2.0, 6.0), look=(0.0, 0.5, 0.0), seed=3):
+    return (Renderer.default().width(w).height(h).samples(spp).use_bvh(use_bvh).seed(seed)
+            .camera(CameraSettings.default().cam_pos(cam).look_at(look).field_of_view(45.0)))
+
+
+def _compare(scene, w, h, spp, use_bvh, min_close=0.995, **kw):
+    ns = NativeScene(scene.to_yaml())
+    orc = OracleScene(scene.to_dict(), use_bvh)
+    r = _renderer(w, h, spp, use_bvh, **kw)
+    p = r.params()
+    go, gd = ns.primary_rays(p, 0)
+    oo, od = orc.primary_rays(p, 0)
+    assert np.array_equal(go, oo) and np.array_equal(gd, od)
+    g = ns.first_hit(go, gd, use_bvh, seed=3)
+    o = orc.first_hit(go, gd, seed=3)
+    assert np.array_equal(g["obj"], o["obj"]) and np.array_equal(g["prim"], o["prim"])
+    assert np.array_equal(g["material"], o["material"])
+    hit = o["obj"] >= 0
+    if hit.any():
+        assert (np.abs(g["t"][hit] - o["t"][hit]) / np.abs(o["t"][hit])).max() <= 1e-5
+    grgb, gsum, gst = ns.render(p)
+    orgb, osum, ost = orc.render(p)
+    close = np.all((np.abs(gsum - osum) <= 1e-4 * np.maximum(np.abs(osum), 1e-3)) | (np.isnan(gsum) & np.isnan(osum)), axis=2)
+    assert close.mean() >= min_close, f"{(~close).sum()} / {close.size} pixels differ"
+    assert gst["samples"] == w * h * spp
+    ns.close()
+    return g, o
+
+
+def _base_scene():
+    s = Scene.new()
+    s.set_environment(SkyEnv.default())
+    return s
+
+
+@pytest.mark.parametrize("use_bvh", [True, False])
+@pytest.mark.parametrize("n_objects", [1, 2, 3])
+def test_tiny_trees(use_bvh, n_objects):
+    """1 object = Leaf root, 2 = DoubleLeaf root, 3 = Branch(Leaf, DoubleLeaf) (bvh.rs:37-69)."""
+    s = _base_scene()
+    m = s.add_material(LambertianMat.with_color(Vec3(0.6, 0.3, 0.2)))
+    g = s.add_material(MetalMat(Vec3(0.8, 0.8, 0.8), 0.1))
+    s.add_object(RenderObject.new(Sphere(1.0, m)).position(0.0, 1.0, 0.0))
+    if n_objects >= 2:
+        s.add_object(RenderObject.new(XZRect(-5.0, 5.0, -5.0, 5.0, 0.0, g)))
+    if n_objects >= 3:
+        s.add_object(RenderObject.new(Sphere(0.5, g)).position(1.5, 0.5, 1.0))
+    _compare(s, 67, 41, 3, use_bvh)
+
+
+@pytest.mark.parametrize("w,h,spp", [(1, 1, 1), (1, 7, 2), (33, 1, 5), (31, 17, 1), (129, 65, 2)])
+def test_ragged_image_sizes(w, h, spp):
+    s = _base_scene()
+    m = s.add_material(LambertianMat(CheckerTexture.with_colors(Vec3(0.1, 0.1, 0.1), Vec3(0.9, 0.9, 0.9), 4.0)))
+    d = s.add_material(DielectricMat(1.5))
+    s.add_object(RenderObject.new(XZRect(-8.0, 8.0, -8.0, 8.0, 0.0, m)))
+    s.add_object(RenderObject.new(Sphere(1.0, d)).position(0.0, 1.0, 0.0))
+    s.add_object(RenderObject.new(Sphere(0.4, m)).position(-1.5, 0.4, 1.0))
+    _compare(s, w, h, spp, True, min_close=0.99 if w * h > 4 else 1.0)
+
+
+@pytest.mark.parametrize("use_bvh", [True, False])
+def test_meshes_small_and_nested_in_media(use_bvh):
+    """1- and 2-triangle meshes (Leaf / DoubleLeaf mesh roots), a mesh with normals + uvs, and ConstantMedium
+    wrapping a mesh and a box (volume.rs generic over the boundary shape)."""
+    s = _base_scene()
+    red = s.add_material(LambertianMat.with_color(Vec3(0.8, 0.2, 0.2)))
+    grey = s.add_material(LambertianMat.with_color(Vec3(0.5, 0.5, 0.5)))
+    s.add_object(RenderObject.new(XZRect(-6.0, 6.0, -6.0, 6.0, 0.0, grey)))
+    tri = TriangleMesh([[0, 0, 0], [1, 0, 0], [0, 1, 0]], [0, 1, 2], None, None, red)
+    s.add_object(RenderObject.new(tri).position(-2.0, 0.2, 0.0))
+    quad = TriangleMesh([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], [0, 1, 2, 0, 2, 3],
+                        [[0, 0, 1]] * 4, [[0, 0], [1, 0], [1, 1], [0, 1]], red)
+    s.add_object(RenderObject.new(quad).position(0.0, 0.2, 0.0).rotate(Rotor3.from_rotation_xz(0.5)))
+    # a closed tetrahedron as medium boundary
+    v = [[0, 0, 0], [1, 0, 0], [0.5, 0, 0.9], [0.5, 0.9, 0.4]]
+    tet = TriangleMesh(v, [0, 2, 1, 0, 1, 3, 1, 2, 3, 2, 0, 3], None, None, red)
+    s.add_volume(RenderObject.new(tet).position(1.5, 0.1, 0.5), 2.0, ConstantTexture(Vec3(0.2, 0.4, 0.9)))
+    s.add_volume(RenderObject.new(Rect3d.with_size(Vec3(1.0, 1.0, 1.0), grey)).position(-0.5, 0.0, -2.5), 1.5,
+                 ConstantTexture(Vec3(0.9, 0.9, 0.9)))
+    _compare(s, 96, 64, 4, use_bvh)
+
+
+@pytest.mark.parametrize("use_bvh", [True, False])
+def test_conics_textures_and_rotations(use_bvh):
+    s = _base_scene()
+    marble = s.add_material(LambertianMat(MarbleTexture(4, 3.0)))
+    perlin = s.add_material(LambertianMat(PerlinNoiseTexture(2.5)))
+    light = s.add_material(EmissiveMat.with_color(Vec3(4.0, 4.0, 4.0)))
+    metal = s.add_material(MetalMat(Vec3(0.7, 0.6, 0.5), 0.3))
+    s.add_object(RenderObject.new(XZRect(-8.0, 8.0, -8.0, 8.0, 0.0, perlin)))
+    s.add_object(RenderObject.new(Cylinder.partial(0.7, 1.5, 270.0, marble)).position(-2.0, 0.0, 0.0)
+                 .rotate(Rotor3.from_rotation_xy(0.4)))
+    s.add_object(RenderObject.new(Cone(0.8, 1.6, metal)).position(0.0, 0.0, 0.5))
+    s.add_object(RenderObject.new(Disk.partial(1.0, 300.0, 0.3, marble)).position(2.0, 0.8, 0.0)
+                 .rotate(Rotor3.from_rotation_yz(0.7)))
+    s.add_object(RenderObject.new(XYRect(-1.0, 1.0, 2.0, 3.0, -2.0, light)).flip_normals())
+    s.add_object(RenderObject.new(YZRect(0.0, 1.0, -1.0, 1.0, 3.0, metal)).rotate(Rotor3.from_rotation_xz(-0.3)))
+    # rotation below the 0.999 cos-trace threshold: the ray is NOT rotated but the hit is (scene.rs:242-258)
+    s.add_object(RenderObject.new(Rect3d.with_size(Vec3(0.6, 0.6, 0.6), marble)).position(0.5, 0.0, 2.0)
+                 .rotate(Rotor3.from_rotation_xz(0.02)))
+    _compare(s, 120, 80, 4, use_bvh, min_close=0.98)   # sin / atan2 / acos heavy: a few more ulp-flipped pixels
+
+
+def test_rect3d_faces_with_their_own_materials():
+    """A deserialised Rect3d may carry a different material per face (rect3d.rs:10-15 stores plain rects)."""
+    s = _base_scene()
+    mats = [s.add_material(LambertianMat.with_color(Vec3(*c))) for c in
+            [(0.9, 0.1, 0.1), (0.1, 0.9, 0.1), (0.1, 0.1, 0.9), (0.9, 0.9, 0.1), (0.1, 0.9, 0.9), (0.9, 0.1, 0.9)]]
+    emis = s.add_material(EmissiveMat.with_color(Vec3(2.0, 2.0, 2.0)))
+    box = Rect3d.with_size(Vec3(1.0, 1.0, 1.0), mats[0])
+    for i, (_tag, face) in enumerate(box.faces):
+        face.material = mats[i] if i != 2 else emis
+    s.add_object(RenderObject.new(box).position(-0.5, 0.0, -0.5).rotate(Rotor3.from_rotation_xz(0.6)))
+    s.add_object(RenderObject.new(XZRect(-5.0, 5.0, -5.0, 5.0, 0.0, mats[3])))
+    for use_bvh in (True, False):
+        g, o = _compare(s, 80, 60, 4, use_bvh)
+        assert len(set(o["material"][o["obj"] == 0].tolist())) >= 2
+
+
+def test_many_objects_deep_tree():
+    """4097 spheres: a 13-level reference tree (7 wide levels); exercises the traversal stack bound."""
+    rng = np.random.default_rng(1)
+    s = _base_scene()
+    m = s.add_material(LambertianMat.with_color(Vec3(0.5, 0.6, 0.7)))
+    for p in rng.uniform(-6, 6, (4097, 3)):
+        s.add_object(RenderObject.new(Sphere(0.12, m)).position(float(p[0]), float(p[1]), float(p[2])))
+    _compare(s, 96, 64, 2, True, cam=(0.0, 0.0, 16.0), look=(0.0, 0.0, 0.0))
+
+
+def test_zero_samples_and_bad_arguments():
+    from firework_b200._native import FireworkError
+    s = _base_scene()
+    m = s.add_material(LambertianMat.with_color(Vec3(0.5, 0.5, 0.5)))
+    s.add_object(RenderObject.new(Sphere(1.0, m)))
+    ns = NativeScene(s.to_yaml())
+    p = _renderer(8, 8, 4, True).params(sample_begin=0, sample_count=0)
+    rgb, sm, st = ns.render(p)
+    assert not sm.any() and st["rays"] == 0
+    bad = _renderer(8, 8, 4, True).params()
+    bad.width = 0
+    with pytest.raises(FireworkError):
+        ns.render(bad)
+    ns.close()

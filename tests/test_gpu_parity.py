@@ -300,3 +300,28 @@ def test_full_size_properties(scenes, name, spp):
     rgb2, s2, _ = ns.render(p)
     assert np.array_equal(s, s2) and np.array_equal(rgb, rgb2)
     assert rgb.shape == (cfg.height, cfg.width, 3) and rgb.std() > 5.0
+
+
+def test_cli_checkpoint_resume(tmp_path, scenes):
+    """src/main.rs equivalent + sample-range checkpointing: an interrupted render resumed from its checkpoint
+    equals the uninterrupted one (same samples; the per-pixel fp32 add of two partial sums is the only difference)."""
+    from firework_b200.__main__ import main
+    from firework_b200.progressive import render_progressive
+    from firework_b200.api import Scene
+    from PIL import Image
+    scene_file = CONFIGS["conics_cli"].path()
+    out = tmp_path / "a.png"
+    ck = tmp_path / "ck.npz"
+    # 6 of 10 samples, then "crash"; resume to 10
+    assert main(["--scene-file", scene_file, "-s", "6", "-o", str(out), "--checkpoint", str(ck), "--chunk", "3",
+                 "--width", "160", "--height", "90"]) == 0
+    assert int(np.load(ck)["done"]) == 6
+    assert main(["--scene-file", scene_file, "-s", "10", "-o", str(out), "--checkpoint", str(ck), "--chunk", "4",
+                 "--width", "160", "--height", "90"]) == 0
+    assert int(np.load(ck)["done"]) == 10
+    resumed = np.asarray(Image.open(out))
+    ns, _ = scenes("conics_cli")
+    whole, s, _ = ns.render(params_for("conics_cli", 160, 90, 10, seed=0))
+    assert resumed.shape == whole.shape
+    assert np.abs(resumed.astype(int) - whole.astype(int)).max() <= 1
+    assert np.allclose(np.load(ck)["sums"], s, rtol=1e-5, atol=1e-6)
