@@ -49,7 +49,8 @@ def load_asset(path: str, kind: str, asset_dir: str | None = None, registry: dic
         return synthetic_hdr(int(w), int(h), int(seed))
     cands = [path]
     if asset_dir:
-        cands = [os.path.join(asset_dir, path), os.path.join(asset_dir, os.path.basename(path)), path]
+        cands = [os.path.join(asset_dir, path), os.path.join(asset_dir, os.path.basename(path)),
+                 os.path.join(asset_dir, "assets", os.path.basename(path)), path]
     for c in cands:
         if os.path.exists(c):
             if kind == "hdr":
