@@ -513,6 +513,33 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
             float4 ro, rd;
             FW_CUDA(cudaMemcpy(&ro, ps.ray_o + worst, 16, cudaMemcpyDeviceToHost));
             FW_CUDA(cudaMemcpy(&rd, ps.ray_d + worst, 16, cudaMemcpyDeviceToHost));
+            if (const char* dump = getenv("FW_DEBUG_DUMP")) {
+                // per-bounce dump for offline coherence analysis: queue order, per-path box tests, rays
+                uint32_t cnt = N;
+                std::vector<uint32_t> hq;
+                if (count_in) {
+                    FW_CUDA(cudaMemcpy(&cnt, count_in, 4, cudaMemcpyDeviceToHost));
+                    hq.resize(cnt);
+                    FW_CUDA(cudaMemcpy(hq.data(), q_in, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+                } else {
+                    hq.resize(cnt);
+                    for (uint32_t i = 0; i < cnt; ++i) hq[i] = i;
+                }
+                std::vector<float4> ho(N), hd(N);
+                FW_CUDA(cudaMemcpy(ho.data(), ps.ray_o, (size_t)N * 16, cudaMemcpyDeviceToHost));
+                FW_CUDA(cudaMemcpy(hd.data(), ps.ray_d, (size_t)N * 16, cudaMemcpyDeviceToHost));
+                std::string fn = std::string(dump) + "_b" + std::to_string(bounce) + ".bin";
+                FILE* f = fopen(fn.c_str(), "wb");
+                if (f) {
+                    fwrite(&cnt, 4, 1, f);
+                    for (uint32_t i = 0; i < cnt; ++i) {
+                        uint32_t pth = hq[i];
+                        float rec[8] = {ho[pth].x, ho[pth].y, ho[pth].z, hd[pth].x, hd[pth].y, hd[pth].z, (float)hs[pth], (float)pth};
+                        fwrite(rec, 4, 8, f);
+                    }
+                    fclose(f);
+                }
+            }
             fprintf(stderr, "[fw debug] bounce %u: box tests total %llu, worst path %zu (pixel %zu sample %zu): %u tests, o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g)\n",
                     bounce, sum, worst, (size_t)b.pix0 + worst % b.npix, (size_t)b.s0 + worst / b.npix, hs[worst], ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
         } else if (use_bvh && sc->flat.has_top_mesh && sc->two_pass) {

@@ -12,6 +12,9 @@
 
 namespace fw {
 
+#ifndef FW_EXTEND_MIN_BLOCKS
+#define FW_EXTEND_MIN_BLOCKS 8   // __launch_bounds__ min blocks / SM of the BVH extend kernels (register cap knob)
+#endif
 constexpr int FW_MAX_DEPTH = 10;          // render.rs:21  `depth < 10`
 constexpr int FW_COUNTERS_PER_BOUNCE = 8; // [0..5] material queues (MatKind), [6] next extend queue, [7] extend work cursor
 
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(128) extend_bvh_debug_kernel(DeviceScene S, Pa
 // against the non-mesh objects and the mesh root boxes; rays that must enter a mesh are compacted into q_mesh
 // (counter slot 7) and finished by pass 2, where every lane of a warp is doing real mesh traversal.
 template <bool NESTED>
-__global__ void __launch_bounds__(128) extend_pass1_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+__global__ void __launch_bounds__(128, FW_EXTEND_MIN_BLOCKS) extend_pass1_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
                                                            const uint32_t* __restrict__ q_in,
                                                            const uint32_t* __restrict__ count_in, uint32_t n_direct,
                                                            uint32_t* counters_out) {
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(128) extend_pass1_kernel(DeviceScene S, PathSt
     }
 }
 template <bool NESTED>
-__global__ void __launch_bounds__(128) extend_pass2_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+__global__ void __launch_bounds__(128, FW_EXTEND_MIN_BLOCKS) extend_pass2_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
                                                            uint32_t* counters_out) {
     uint32_t total = counters_out[7];
     const uint32_t* __restrict__ q_in = ps.q_mesh;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(128) extend_pass2_kernel(DeviceScene S, PathSt
 }
 
 template <bool NESTED, bool MESHES>
-__global__ void __launch_bounds__(128) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+__global__ void __launch_bounds__(128, FW_EXTEND_MIN_BLOCKS) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
                                                                 const uint32_t* __restrict__ q_in,
                                                                 const uint32_t* __restrict__ count_in, uint32_t n_direct,
                                                                 uint32_t* counters_out) {
