@@ -307,6 +307,15 @@ def main():
             hbm_peak = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             hbm_peak = 6650.0
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this very
+        # command (profiles/r01_extend_traffic_<workload>.json, written by tools/ncu_traffic.py); null if absent
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(REPO, "profiles", f"r01_extend_traffic_{cfg.name}.json")))
+            if spp == cfg.samples and width == cfg.width and height == cfg.height:
+                traffic = tj["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         line = dict(base)
         line.update({
             "value": value, "mrays_per_s": mrays, "ms_per_step": ms_total / args.steps,
@@ -316,7 +325,7 @@ def main():
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "fp32", "kernel": "extend_kernel", "achieved": ach_tflops, "peak": peaks["fp32_tflops"],
-                         "unit": "TFLOP/s", "frac": ach_tflops / peaks["fp32_tflops"], "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach_tflops / peaks["fp32_tflops"], "traffic": traffic,
                          "peak_source": "FP32 FMA microbenchmark on this GPU in this run (fw_measure_peaks); MEASURED_PEAKS.json has no FP32 figure",
                          "flops_per_ray": flops_ray, "rays_per_launch": my_rays / max(totals["extend_launches"], 1),
                          "avg_launch_ms": totals["ms_extend"] / max(totals["extend_launches"], 1),
