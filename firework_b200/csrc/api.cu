@@ -292,13 +292,23 @@ int fw_scene_commit(fw_scene* sc, int device) {
     if (device < 0 || device >= ndev) return set_error(FW_ERR_CUDA, "no such CUDA device " + std::to_string(device));
     sc->device = device;
     FW_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    FW_CUDA(cudaGetDeviceProperties(&prop, device));
-    sc->sm_count = prop.multiProcessorCount;
     {
-        int nb = 0;
-        FW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extend_bvh_persistent_kernel<false, true>, 128, 0));
-        sc->bvh_blocks_per_sm = std::max(nb, 1);
+        // device facts are queried once per device (cudaGetDeviceProperties costs milliseconds)
+        static std::mutex info_mutex;
+        static int cached_sm[64], cached_blocks[64];
+        static bool cached[64] = {false};
+        std::lock_guard<std::mutex> lk(info_mutex);
+        if (device < 64 && cached[device]) {
+            sc->sm_count = cached_sm[device];
+            sc->bvh_blocks_per_sm = cached_blocks[device];
+        } else {
+            int smc = 0, nb = 0;
+            FW_CUDA(cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device));
+            FW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extend_bvh_persistent_kernel<false, true>, 128, 0));
+            sc->sm_count = smc;
+            sc->bvh_blocks_per_sm = std::max(nb, 1);
+            if (device < 64) { cached_sm[device] = sc->sm_count; cached_blocks[device] = sc->bvh_blocks_per_sm; cached[device] = true; }
+        }
     }
     {
         int crc = acquire_ctx(device, &sc->ctx);
