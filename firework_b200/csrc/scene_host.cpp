@@ -566,6 +566,28 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
     out.shapes = desc.shapes;
     out.mats = desc.mats;
     out.texs = desc.texs;
+    // Rect3d: the device copy carries a PADDED box around the union of its faces in f[0..5] (lo xyz, hi xyz).
+    // The kernels use it as a conservative pre-test before the six face tests (rect3d.rs:89-100): a face can only
+    // be hit inside that box, and the padding (1e-3 of the extent + 1e-4) dwarfs every rounding difference
+    // between the slab arithmetic and the face test, so skipping the faces when the box is missed never changes
+    // a result.  (pos / size themselves are only needed for the object's bounding box, computed below from desc.)
+    for (ShapeRec& s : out.shapes) {
+        if (s.kind != SH_RECT3D) continue;
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        static const int A1[3] = {0, 0, 1}, A2[3] = {1, 2, 2}, AK[3] = {2, 1, 0};
+        for (int f = 0; f < s.i1; ++f) {
+            const ShapeRec& r = desc.shapes[s.i0 + f];
+            int p = r.i0 & 3;
+            lo[A1[p]] = fminf(lo[A1[p]], r.f[0]); hi[A1[p]] = fmaxf(hi[A1[p]], r.f[2]);
+            lo[A2[p]] = fminf(lo[A2[p]], r.f[1]); hi[A2[p]] = fmaxf(hi[A2[p]], r.f[3]);
+            lo[AK[p]] = fminf(lo[AK[p]], r.f[4]); hi[AK[p]] = fmaxf(hi[AK[p]], r.f[4]);
+        }
+        float ext = 0.0f;
+        for (int a = 0; a < 3; ++a) ext = fmaxf(ext, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+        float pad = 1e-3f * ext + 1e-4f;
+        if (!(ext < INFINITY)) pad = 0.0f;  // no faces / non-finite: the inverted or infinite box decides
+        for (int a = 0; a < 3; ++a) { s.f[a] = lo[a] - pad; s.f[3 + a] = hi[a] + pad; }
+    }
     {
         // uv is read only by ImageTexture::sample (texture.rs:296-309); checker forwards it to its children
         std::function<bool(int, int)> reads_uv = [&](int t, int depth) -> bool {
