@@ -41,11 +41,11 @@ struct RenderCtx {
     bool in_use = false;
     PathState ps{};
     size_t ps_cap = 0;
+    size_t ps_nseg_max = 0;
     cudaStream_t stream = nullptr;
     float* d_sum = nullptr;
     unsigned char* d_rgb = nullptr;
     size_t d_sum_pix = 0;
-    uint32_t* h_counters = nullptr;  // pinned (debug read-backs)
     unsigned long long* d_rays = nullptr;   // device-side ray tally of the current render call
     unsigned long long* h_rays = nullptr;   // pinned
     std::vector<cudaEvent_t> ev_pool;
@@ -62,13 +62,10 @@ struct fw_scene {
     bool committed = false;  // uploaded to the device
     int device = 0;
     int sm_count = 148;
-    int bvh_blocks_per_sm = 4;
-    int extend_mode = 0;     // 0 = grid-stride extend on every bounce (default: measured fastest); 1 = persistent dynamic-fetch extend from bounce
-                             // `persistent_from_bounce` on (knobs: FW_EXTEND_MODE, FW_PERSISTENT_FROM, FW_REFILL_LANES)
-    int persistent_from_bounce = 1;
     int two_pass = 1;        // two-pass extend for BVH scenes with top-level meshes (FW_TWO_PASS)
-    int refill_lanes = FW_REFILL_LANES;
     DeviceScene dscene{};
+    LinProgram lin_prog{};     // linear-scan program, passed to the kernels by value (kernel-parameter space)
+    bool lin_prog_ok = false;  // the scene's program fits FW_LIN_MAX_WORDS (else: object-loop kernels)
     std::vector<void*> allocs;
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> texobjs;
@@ -99,7 +96,6 @@ static void destroy_ctx(RenderCtx* c) {
     fr(c->ps.radiance); fr(c->ps.q_extend[0]); fr(c->ps.q_extend[1]); fr(c->ps.q_mesh); fr(c->ps.counters);
     for (int k = 0; k < MAT_NUM_QUEUES; ++k) fr(c->ps.q_mat[k]);
     fr(c->d_sum); fr(c->d_rgb);
-    if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_rays) cudaFreeHost(c->h_rays);
     if (c->d_rays) cudaFree(c->d_rays);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -125,7 +121,6 @@ static int acquire_ctx(int device, RenderCtx** out) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_end);
-    if (e == cudaSuccess) e = cudaMallocHost(&c->h_counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_COUNTERS_PER_BOUNCE);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_rays, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_rays, sizeof(unsigned long long));
     if (e != cudaSuccess) {
@@ -295,19 +290,16 @@ int fw_scene_commit(fw_scene* sc, int device) {
     {
         // device facts are queried once per device (cudaGetDeviceProperties costs milliseconds)
         static std::mutex info_mutex;
-        static int cached_sm[64], cached_blocks[64];
+        static int cached_sm[64];
         static bool cached[64] = {false};
         std::lock_guard<std::mutex> lk(info_mutex);
         if (device < 64 && cached[device]) {
             sc->sm_count = cached_sm[device];
-            sc->bvh_blocks_per_sm = cached_blocks[device];
         } else {
-            int smc = 0, nb = 0;
+            int smc = 0;
             FW_CUDA(cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device));
-            FW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extend_bvh_persistent_kernel<false, true>, 128, 0));
             sc->sm_count = smc;
-            sc->bvh_blocks_per_sm = std::max(nb, 1);
-            if (device < 64) { cached_sm[device] = sc->sm_count; cached_blocks[device] = sc->bvh_blocks_per_sm; cached[device] = true; }
+            if (device < 64) { cached_sm[device] = sc->sm_count; cached[device] = true; }
         }
     }
     {
@@ -358,6 +350,10 @@ int fw_scene_commit(fw_scene* sc, int device) {
     D.nan_bvh_obj = F.nan_bvh_obj; D.nan_bvh_prim = F.nan_bvh_prim;
     D.nan_lin_obj = F.nan_lin_obj; D.nan_lin_prim = F.nan_lin_prim;
     for (const MatRec& m : F.mats) sc->mat_present[m.kind] = true;
+    sc->lin_prog_ok = F.lin_words.size() <= (size_t)FW_LIN_MAX_WORDS;
+    if (const char* e = getenv("FW_LINEAR_PROGRAM")) sc->lin_prog_ok = sc->lin_prog_ok && atoi(e) != 0;
+    memset(&sc->lin_prog, 0, sizeof(sc->lin_prog));
+    if (sc->lin_prog_ok) memcpy(sc->lin_prog.w, F.lin_words.data(), F.lin_words.size() * sizeof(float4));
     sc->committed = true;
     return FW_OK;
 }
@@ -391,6 +387,12 @@ int fw_scene_mesh_leaf_order(const fw_scene* sc, int obj, int* out, int cap) {
             out[i] = t;
         }
     return m.tri_count;
+}
+int fw_scene_linear_program(const fw_scene* sc, float* out, int cap) {
+    if (!sc || !sc->built) return set_error(FW_ERR_STATE, "scene not built (fw_scene_build_host / fw_scene_commit)");
+    int n = (int)sc->flat.lin_words.size();
+    if (out) memcpy(out, sc->flat.lin_words.data(), sizeof(float4) * (size_t)std::max(0, std::min(n, cap)));
+    return n;
 }
 int fw_material_texture(const fw_scene* sc, int material) {
     if (!sc || material < 0 || material >= (int)sc->desc.mats.size()) return -1;
@@ -431,9 +433,21 @@ int fw_set_batch_paths(fw_scene* sc, uint64_t paths) {
 // ----------------------------------------------------------------------------------------------------------
 // wavefront orchestration
 // ----------------------------------------------------------------------------------------------------------
+// Segment geometry of a batch of `n` paths (wavefront.cuh "segmented queues"): enough segments to give every SM
+// several blocks, few enough that a segment still holds whole tiles.
+static constexpr uint32_t FW_SEG_PER_SM_MAX = 64;
+static void segment_geometry(const fw_scene* sc, size_t n, uint32_t* nseg, uint32_t* seg_cap) {
+    size_t tiles = (n + FW_TILE - 1) / FW_TILE;
+    size_t want = std::max<size_t>((size_t)sc->sm_count, std::min<size_t>((size_t)sc->sm_count * 32, tiles / 8));  // measured: sm x 32 (FW_SEGMENTS sweep, profiles/r01e)
+    if (const char* e = getenv("FW_SEGMENTS")) want = std::max<size_t>(1, std::min<size_t>((size_t)sc->sm_count * FW_SEG_PER_SM_MAX, strtoull(e, nullptr, 10)));
+    *nseg = (uint32_t)want;
+    *seg_cap = (uint32_t)(((tiles + want - 1) / want) * FW_TILE);
+}
+
 static int ensure_path_state(fw_scene* sc, size_t cap) {
     RenderCtx* ctx = sc->ctx;
-    if (ctx->ps_cap >= cap) {
+    const size_t nseg_max = (size_t)sc->sm_count * FW_SEG_PER_SM_MAX;
+    if (ctx->ps_cap >= cap && ctx->ps_nseg_max >= nseg_max) {
         ctx->ps.cap = (uint32_t)ctx->ps_cap;
         return FW_OK;
     }
@@ -443,19 +457,22 @@ static int ensure_path_state(fw_scene* sc, size_t cap) {
     fr(ps.q_extend[0]); fr(ps.q_extend[1]); fr(ps.q_mesh); fr(ps.counters);
     for (int k = 0; k < MAT_NUM_QUEUES; ++k) fr(ps.q_mat[k]);
     ctx->ps_cap = 0;
+    // queue regions: nseg * seg_cap <= n + nseg * FW_TILE slots for any batch of n <= cap paths
+    const size_t qcap = cap + (nseg_max + 1) * FW_TILE;
     FW_CUDA(cudaMalloc(&ps.ray_o, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.ray_d, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.win_a, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.win_b, cap * sizeof(float4)));
     FW_CUDA(cudaMalloc(&ps.atten, cap * sizeof(float4) * FW_MAX_DEPTH));
     FW_CUDA(cudaMalloc(&ps.radiance, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.q_extend[0], cap * sizeof(uint32_t)));
-    FW_CUDA(cudaMalloc(&ps.q_extend[1], cap * sizeof(uint32_t)));
-    FW_CUDA(cudaMalloc(&ps.q_mesh, cap * sizeof(uint32_t)));
-    for (int k = 0; k < MAT_NUM_QUEUES; ++k) FW_CUDA(cudaMalloc(&ps.q_mat[k], cap * sizeof(uint32_t)));
-    FW_CUDA(cudaMalloc(&ps.counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_COUNTERS_PER_BOUNCE));
+    FW_CUDA(cudaMalloc(&ps.q_extend[0], qcap * sizeof(uint32_t)));
+    FW_CUDA(cudaMalloc(&ps.q_extend[1], qcap * sizeof(uint32_t)));
+    FW_CUDA(cudaMalloc(&ps.q_mesh, qcap * sizeof(uint32_t)));
+    for (int k = 0; k < MAT_NUM_QUEUES; ++k) FW_CUDA(cudaMalloc(&ps.q_mat[k], qcap * sizeof(uint32_t)));
+    FW_CUDA(cudaMalloc(&ps.counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * nseg_max));
     ps.cap = (uint32_t)cap;
     ctx->ps_cap = cap;
+    ctx->ps_nseg_max = nseg_max;
     return FW_OK;
 }
 
@@ -485,18 +502,14 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
     PathState& ps = sc->ctx->ps;
     const DeviceScene& S = sc->dscene;
     uint32_t N = b.npix * b.ns;
-    const size_t counter_bytes = sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_COUNTERS_PER_BOUNCE;
+    segment_geometry(sc, N, &ps.nseg, &ps.seg_cap);
+    const size_t counter_bytes = sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * (size_t)ps.nseg;
     FW_CUDA(cudaMemsetAsync(ps.counters, 0, counter_bytes, st));
     unsigned sm = (unsigned)sc->sm_count;
-    raygen_kernel<<<grid_for(N, 256, sm * 8), 256, 0, st>>>(cam, b, seed, ps);
+    const unsigned G = ps.nseg;   // one block per segment, in every queue-driven kernel
+    raygen_kernel<<<G, FW_BLOCK, 0, st>>>(cam, b, seed, ps);
     tot.launches++;
-    unsigned g_ext = grid_for(N, 128, sm * 16);
-    unsigned g_bvh = grid_for(N, 128, sm * (unsigned)sc->bvh_blocks_per_sm);  // persistent: one resident wave
-    unsigned g_sh = grid_for(N, 256, sm * 8);
     for (uint32_t bounce = 0; bounce <= (uint32_t)FW_MAX_DEPTH; ++bounce) {
-        uint32_t* row = ps.counters + bounce * FW_COUNTERS_PER_BOUNCE;
-        const uint32_t* q_in = bounce == 0 ? nullptr : ps.q_extend[bounce & 1];
-        const uint32_t* count_in = bounce == 0 ? nullptr : (ps.counters + (bounce - 1) * FW_COUNTERS_PER_BOUNCE + 6);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (sc->profiling) {
             int rc;
@@ -512,29 +525,38 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
                 FW_CUDA(cudaMalloc(&d_steps, (size_t)ps.cap * 4));
                 d_steps_cap = ps.cap;
             }
-            FW_CUDA(cudaMemsetAsync(d_steps, 0, (size_t)ps.cap * 4, st));
-            extend_bvh_debug_kernel<<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, d_steps);
+            FW_CUDA(cudaMemsetAsync(d_steps, 0xff, (size_t)ps.cap * 4, st));   // 0xffffffff = path not traced this bounce
+            extend_bvh_debug_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, d_steps);
             FW_CUDA(cudaStreamSynchronize(st));
-            std::vector<uint32_t> hs(ps.cap);
-            FW_CUDA(cudaMemcpy(hs.data(), d_steps, (size_t)ps.cap * 4, cudaMemcpyDeviceToHost));
+            std::vector<uint32_t> hs(N);
+            FW_CUDA(cudaMemcpy(hs.data(), d_steps, (size_t)N * 4, cudaMemcpyDeviceToHost));
             size_t worst = 0;
             unsigned long long sum = 0;
-            for (size_t i = 0; i < N; ++i) { sum += hs[i]; if (hs[i] > hs[worst]) worst = i; }
+            bool any = false;
+            for (size_t i = 0; i < N; ++i) {
+                if (hs[i] == 0xffffffffu) continue;
+                sum += hs[i];
+                if (!any || hs[i] > hs[worst]) { worst = i; any = true; }
+            }
             float4 ro, rd;
             FW_CUDA(cudaMemcpy(&ro, ps.ray_o + worst, 16, cudaMemcpyDeviceToHost));
             FW_CUDA(cudaMemcpy(&rd, ps.ray_d + worst, 16, cudaMemcpyDeviceToHost));
             if (const char* dump = getenv("FW_DEBUG_DUMP")) {
                 // per-bounce dump for offline coherence analysis: queue order, per-path box tests, rays
-                uint32_t cnt = N;
                 std::vector<uint32_t> hq;
-                if (count_in) {
-                    FW_CUDA(cudaMemcpy(&cnt, count_in, 4, cudaMemcpyDeviceToHost));
-                    hq.resize(cnt);
-                    FW_CUDA(cudaMemcpy(hq.data(), q_in, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
-                } else {
-                    hq.resize(cnt);
-                    for (uint32_t i = 0; i < cnt; ++i) hq[i] = i;
+                {
+                    std::vector<uint32_t> cnts(ps.nseg);
+                    FW_CUDA(cudaMemcpy(cnts.data(), ps.counters + ((size_t)bounce * FW_NUM_QUEUES + FW_Q_EXTEND) * ps.nseg,
+                                       (size_t)ps.nseg * 4, cudaMemcpyDeviceToHost));
+                    std::vector<uint32_t> region(ps.seg_cap);
+                    for (uint32_t seg = 0; seg < ps.nseg; ++seg) {
+                        if (!cnts[seg]) continue;
+                        FW_CUDA(cudaMemcpy(region.data(), ps.q_extend[bounce & 1] + (size_t)seg * ps.seg_cap, (size_t)cnts[seg] * 4,
+                                           cudaMemcpyDeviceToHost));
+                        hq.insert(hq.end(), region.begin(), region.begin() + cnts[seg]);
+                    }
                 }
+                uint32_t cnt = (uint32_t)hq.size();
                 std::vector<float4> ho(N), hd(N);
                 FW_CUDA(cudaMemcpy(ho.data(), ps.ray_o, (size_t)N * 16, cudaMemcpyDeviceToHost));
                 FW_CUDA(cudaMemcpy(hd.data(), ps.ray_d, (size_t)N * 16, cudaMemcpyDeviceToHost));
@@ -551,36 +573,40 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
                 }
             }
             fprintf(stderr, "[fw debug] bounce %u: box tests total %llu, worst path %zu (pixel %zu sample %zu): %u tests, o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g)\n",
-                    bounce, sum, worst, (size_t)b.pix0 + worst % b.npix, (size_t)b.s0 + worst / b.npix, hs[worst], ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
+                    bounce, sum, worst, (size_t)b.pix0 + worst % b.npix, (size_t)b.s0 + worst / b.npix, any ? hs[worst] : 0u, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
         } else if (use_bvh && sc->flat.has_top_mesh && sc->two_pass) {
             if (sc->flat.has_medium_mesh) {
-                extend_pass1_kernel<true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
-                extend_pass2_kernel<true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, row);
+                extend_pass1_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+                extend_pass2_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
             } else {
-                extend_pass1_kernel<false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
-                extend_pass2_kernel<false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, row);
+                extend_pass1_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+                extend_pass2_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
             }
             tot.launches++;
-        } else if (use_bvh && (sc->extend_mode == 0 || (int)bounce < sc->persistent_from_bounce)) {
-            if (sc->flat.has_medium_mesh)
-                extend_bvh_simple_kernel<true, true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
-            else if (sc->flat.has_mesh)
-                extend_bvh_simple_kernel<false, true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
-            else
-                extend_bvh_simple_kernel<false, false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
         } else if (use_bvh) {
             if (sc->flat.has_medium_mesh)
-                extend_bvh_persistent_kernel<true, true><<<g_bvh, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, sc->refill_lanes);
+                extend_bvh_simple_kernel<true, true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
             else if (sc->flat.has_mesh)
-                extend_bvh_persistent_kernel<false, true><<<g_bvh, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, sc->refill_lanes);
+                extend_bvh_simple_kernel<false, true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
             else
-                extend_bvh_persistent_kernel<false, false><<<g_bvh, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row, sc->refill_lanes);
-            classify_kernel<<<g_sh, 256, 0, st>>>(S, ps, q_in, count_in, N, row);
-            tot.launches++;
+                extend_bvh_simple_kernel<false, false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+        } else if (sc->lin_prog_ok) {
+            const LinProgram& P = sc->lin_prog;
+            if (sc->flat.lin_generic) {
+                if (sc->flat.has_mesh)
+                    extend_linear_prog_kernel<true, true, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+                else
+                    extend_linear_prog_kernel<true, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+            } else if (bounce == 0) {
+                // coherent primary rays: whole warps skip Rect3d boxes they do not enter (PRETEST)
+                extend_linear_prog_kernel<false, false, true><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+            } else {
+                extend_linear_prog_kernel<false, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+            }
         } else if (sc->flat.has_mesh) {
-            extend_linear_kernel<true><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+            extend_linear_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
         } else {
-            extend_linear_kernel<false><<<g_ext, 128, 0, st>>>(S, ps, b, seed, bounce, q_in, count_in, N, row);
+            extend_linear_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
         }
         if (sc->profiling) {
             FW_CUDA(cudaEventRecord(e1, st));
@@ -588,35 +614,34 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
         }
         tot.launches++;
         tot.extend_launches++;
-        miss_kernel<<<g_sh, 256, 0, st>>>(S, ps, bounce, row);
+        miss_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, bounce);
         tot.launches++;
         if (sc->mat_present[MAT_EMISSIVE]) {
-            shade_emissive_kernel<<<g_sh, 256, 0, st>>>(S, ps, bounce, row);
+            shade_emissive_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, bounce);
             tot.launches++;
         }
         if (bounce < (uint32_t)FW_MAX_DEPTH) {
-            uint32_t* q_out = ps.q_extend[(bounce + 1) & 1];
             if (sc->mat_present[MAT_LAMBERTIAN]) {
-                shade_scatter_kernel<MAT_LAMBERTIAN><<<g_sh, 256, 0, st>>>(S, ps, b, seed, bounce, row, q_out, row);
+                shade_scatter_kernel<MAT_LAMBERTIAN><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
                 tot.launches++;
             }
             if (sc->mat_present[MAT_METAL]) {
-                shade_scatter_kernel<MAT_METAL><<<g_sh, 256, 0, st>>>(S, ps, b, seed, bounce, row, q_out, row);
+                shade_scatter_kernel<MAT_METAL><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
                 tot.launches++;
             }
             if (sc->mat_present[MAT_DIELECTRIC]) {
-                shade_scatter_kernel<MAT_DIELECTRIC><<<g_sh, 256, 0, st>>>(S, ps, b, seed, bounce, row, q_out, row);
+                shade_scatter_kernel<MAT_DIELECTRIC><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
                 tot.launches++;
             }
             if (sc->mat_present[MAT_ISOTROPIC]) {
-                shade_scatter_kernel<MAT_ISOTROPIC><<<g_sh, 256, 0, st>>>(S, ps, b, seed, bounce, row, q_out, row);
+                shade_scatter_kernel<MAT_ISOTROPIC><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
                 tot.launches++;
             }
         }
     }
     accumulate_kernel<<<grid_for(b.npix, 256, sm * 8), 256, 0, st>>>(d_sum, ps, b);
     tot.launches++;
-    tally_kernel<<<1, 32, 0, st>>>(ps.counters, N, sc->ctx->d_rays);
+    tally_kernel<<<1, 256, 0, st>>>(ps, sc->ctx->d_rays);
     tot.launches++;
     FW_CUDA(cudaGetLastError());
     return FW_OK;
@@ -638,10 +663,7 @@ static int render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStrea
     // from 4 Mi to 32 Mi paths); ~280 B of state per path -> 9 GB, small next to 180 GB of HBM.
     size_t cap = sc->batch_paths ? sc->batch_paths : ((size_t)1 << 25);
     if (const char* e = getenv("FW_BATCH_PATHS")) cap = std::max<size_t>(1024, strtoull(e, nullptr, 10));
-    if (const char* e = getenv("FW_EXTEND_MODE")) sc->extend_mode = atoi(e);
     if (const char* e = getenv("FW_TWO_PASS")) sc->two_pass = atoi(e);
-    if (const char* e = getenv("FW_PERSISTENT_FROM")) sc->persistent_from_bounce = atoi(e);
-    if (const char* e = getenv("FW_REFILL_LANES")) sc->refill_lanes = std::max(1, std::min(32, atoi(e)));
     cap = std::min<size_t>(cap, npix * std::max<uint32_t>(p->sample_count, 1));
     cap = std::max<size_t>(cap, 32);
     int rc;
@@ -780,6 +802,14 @@ int fw_first_hit(fw_scene* sc, int use_bvh, uint64_t seed, uint32_t n, const flo
         first_hit_probe<true><<<g, 128, 0, sc->ctx->stream>>>(sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
                                                          pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,
                                                          bounce ? dB.as<uint32_t>() : nullptr, out);
+    else if (sc->lin_prog_ok && sc->flat.lin_generic)
+        first_hit_prog_probe<true><<<g, 128, 0, sc->ctx->stream>>>(sc->lin_prog, sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
+                                                              pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,
+                                                              bounce ? dB.as<uint32_t>() : nullptr, out);
+    else if (sc->lin_prog_ok)
+        first_hit_prog_probe<false><<<g, 128, 0, sc->ctx->stream>>>(sc->lin_prog, sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
+                                                               pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,
+                                                               bounce ? dB.as<uint32_t>() : nullptr, out);
     else
         first_hit_probe<false><<<g, 128, 0, sc->ctx->stream>>>(sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
                                                           pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,

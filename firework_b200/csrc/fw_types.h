@@ -32,6 +32,25 @@ enum MatKind : int {  // material.rs; MAT_MISS is a queue id only
 enum TexKind : int { TEX_CONSTANT = 0, TEX_CHECKER = 1, TEX_PERLIN = 2, TEX_TURBULENCE = 3, TEX_MARBLE = 4, TEX_IMAGE = 5 };
 enum EnvKind : int { ENV_COLOR = 0, ENV_SKY = 1, ENV_HDR = 2 };
 
+// Linear-scan program (Renderer.use_bvh == false, scene.rs:137-149).  The scene's objects, in scene order, are
+// compiled host-side into a short list of float4 words that travels in KERNEL PARAMETER space (constant bank):
+// every lane of a warp is at the same item, so the words are fetched through the uniform datapath and the item
+// switch is a uniform branch — no per-lane loads of object / shape records at all.  word0.y = type | plane << 8.
+enum LinItem : int {   // one bit per type: the dispatch is a chain of bit tests, most frequent first
+    LIN_END = 0,
+    LIN_RECT = 1,      // 2 words: (k, type | plane << 8, obj, prim), (min1, min2, max1, max2)           (rect.rs:48-62)
+    LIN_BOX6 = 2,      // 4 words: a Rect3d whose six faces are the canonical ones of Rect3d::new (rect3d.rs:18-80):
+                       //          (lo.x, type, obj, lo.y), (lo.z, hi.x, hi.y, hi.z), padded box (lo.xyz, hi.x), (hi.y, hi.z, -, -)
+    LIN_XFORM_T = 4,   // 1 word : (pos.x, type, pos.y, pos.z): current ray = (o - pos, d)              (scene.rs:250-252)
+    LIN_XFORM_R = 8,   // 4 words: same, then 3 columns of inv_rotation_mat: both rotated                (scene.rs:246-249)
+    LIN_SPHERE = 16,   // 1 word : (radius, type, obj, -)                                               (sphere.rs:32-50)
+    LIN_GENERIC = 32,  // 1 word : (-, type, obj, -): any other object, through object_test on the world ray
+};
+constexpr int FW_LIN_MAX_WORDS = 160;   // 2.5 KiB of the 4 KiB kernel-parameter space
+struct LinProgram {
+    float4 w[FW_LIN_MAX_WORDS];
+};
+
 constexpr int OBJ_KIND_MASK = 0xff;
 constexpr int OBJ_ROTATED = 1 << 8;   // cos_trace < 0.999 (scene.rs:242-246): ray is rotated into object space
 constexpr int OBJ_FLIP = 1 << 9;      // RenderObject.flip_normals (scene.rs:259-261)

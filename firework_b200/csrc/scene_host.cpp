@@ -759,6 +759,74 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         if (obj_unbounded[i]) out.has_unbounded = true;
     }
 
+    // linear-scan program (fw_types.h LinItem): the objects in scene order (scene.rs:137-149)
+    {
+        std::vector<float4>& W = out.lin_words;
+        bool world = true;            // the kernel starts in world space (position +0, unrotated)
+        int space_obj = -1;           // object whose transform defines the current space (when !world)
+        auto bits_eq = [](float a, float b) { return memcmp(&a, &b, 4) == 0; };
+        auto is_pzero = [](float a) { uint32_t u; memcpy(&u, &a, 4); return u == 0u; };  // +0.0 only: x - (+0) == x exactly
+        for (size_t i = 0; i < nobj; ++i) {
+            const ObjectDesc& o = desc.objects[i];
+            const ShapeRec& s = out.shapes[o.shape];  // device copy: Rect3d carries its padded face box
+            bool rotated = (out.obj_meta[i].x & OBJ_ROTATED) != 0;
+            bool simple = s.kind == SH_RECT || s.kind == SH_RECT3D || s.kind == SH_SPHERE;
+            if (!simple) {
+                out.lin_generic = true;
+                W.push_back(float4{0, as_float(LIN_GENERIC), as_float((int)i), 0});
+                continue;
+            }
+            // ray -> object space (scene.rs:242-253), shared with the previous object when the transform is the same
+            bool want_world = !rotated && is_pzero(o.position.x) && is_pzero(o.position.y) && is_pzero(o.position.z);
+            bool same = false;
+            if (want_world) same = world;
+            else if (!world && space_obj >= 0 && !rotated && !(out.obj_meta[space_obj].x & OBJ_ROTATED)) {
+                const ObjectDesc& q = desc.objects[space_obj];
+                same = bits_eq(q.position.x, o.position.x) && bits_eq(q.position.y, o.position.y) && bits_eq(q.position.z, o.position.z);
+            }
+            if (!same) {
+                W.push_back(float4{o.position.x, as_float(rotated ? LIN_XFORM_R : LIN_XFORM_T), o.position.y, o.position.z});
+                if (rotated) for (int c = 0; c < 3; ++c) W.push_back(out.obj_irot[3 * i + c]);
+                world = want_world;
+                space_obj = (int)i;
+            }
+            if (s.kind == SH_SPHERE) {
+                W.push_back(float4{s.f[0], as_float(LIN_SPHERE), as_float((int)i), 0});
+            } else if (s.kind == SH_RECT) {
+                W.push_back(float4{s.f[4], as_float(LIN_RECT | ((s.i0 & 3) << 8)), as_float((int)i), as_float(0)});
+                W.push_back(float4{s.f[0], s.f[1], s.f[2], s.f[3]});
+            } else {
+                // Rect3d: the six canonical faces of Rect3d::new (rect3d.rs:18-80) collapse into one BOX6 item
+                const ShapeRec* f = &desc.shapes[s.i0];
+                bool canon = s.i1 == 6;
+                static const int planes[6] = {0, 0, 1, 1, 2, 2};
+                for (int k = 0; canon && k < 6; ++k) canon = (f[k].kind == SH_RECT) && ((f[k].i0 & 3) == planes[k]);
+                float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+                if (canon) {
+                    lo[0] = f[0].f[0]; lo[1] = f[0].f[1]; hi[0] = f[0].f[2]; hi[1] = f[0].f[3]; hi[2] = f[0].f[4]; lo[2] = f[1].f[4];
+                    // face k: (min1, min2, max1, max2, k) expected from lo / hi
+                    const float exp[6][5] = {{lo[0], lo[1], hi[0], hi[1], hi[2]}, {lo[0], lo[1], hi[0], hi[1], lo[2]},
+                                             {lo[0], lo[2], hi[0], hi[2], hi[1]}, {lo[0], lo[2], hi[0], hi[2], lo[1]},
+                                             {lo[1], lo[2], hi[1], hi[2], hi[0]}, {lo[1], lo[2], hi[1], hi[2], lo[0]}};
+                    for (int k = 0; canon && k < 6; ++k)
+                        for (int c = 0; canon && c < 5; ++c) canon = bits_eq(f[k].f[c], exp[k][c]);
+                }
+                if (canon) {
+                    W.push_back(float4{lo[0], as_float(LIN_BOX6), as_float((int)i), lo[1]});
+                    W.push_back(float4{lo[2], hi[0], hi[1], hi[2]});
+                    W.push_back(float4{s.f[0], s.f[1], s.f[2], s.f[3]});
+                    W.push_back(float4{s.f[4], s.f[5], 0, 0});
+                } else {
+                    for (int k = 0; k < s.i1; ++k) {
+                        W.push_back(float4{f[k].f[4], as_float(LIN_RECT | ((f[k].i0 & 3) << 8)), as_float((int)i), as_float(k)});
+                        W.push_back(float4{f[k].f[0], f[k].f[1], f[k].f[2], f[k].f[3]});
+                    }
+                }
+            }
+        }
+        W.push_back(float4{0, as_float(LIN_END), 0, 0});
+    }
+
     // top-level BVH (bvh.rs:79-98), always built: linear-scan renders simply do not use it
     FlatBVH top;
     if (!build_bvh(out.obj_aabb, top, err, &obj_unbounded)) return false;

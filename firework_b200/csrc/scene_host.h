@@ -74,6 +74,8 @@ bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& er
 struct HostFlat {
     std::vector<float4> nodes;
     std::vector<int> top_items;
+    std::vector<float4> lin_words;  // linear-scan program (fw_types.h LinItem), END-terminated
+    bool lin_generic = false;       // the program contains LIN_GENERIC items
     std::vector<float4> obj_posr, leaf_posr;
     std::vector<int4> obj_meta, leaf_meta;
     std::vector<float4> obj_rot, obj_irot;

@@ -16,8 +16,17 @@ namespace fw {
 #define FW_EXTEND_MIN_BLOCKS 8   // __launch_bounds__ min blocks / SM of the BVH extend kernels (register cap knob)
 #endif
 constexpr int FW_MAX_DEPTH = 10;          // render.rs:21  `depth < 10`
-constexpr int FW_COUNTERS_PER_BOUNCE = 8; // [0..5] material queues (MatKind), [6] next extend queue, [7] extend work cursor
+constexpr int FW_NUM_QUEUES = 8;          // [0..5] material queues (MatKind), [6] next extend queue, [7] mesh queue (two-pass extend)
+constexpr int FW_Q_EXTEND = 6, FW_Q_MESH = 7;
+constexpr int FW_TILE = 128;              // paths per tile: bounce 0 deals tiles round-robin to the segments
+constexpr int FW_BLOCK = 128;             // threads per block of every queue-driven kernel
 
+// Queues are SEGMENTED: each of the `nseg` segments owns a fixed region of `seg_cap` slots in every queue and is
+// processed by exactly one thread block per kernel, which is also the only writer of that segment's regions in
+// the kernel's output queues.  A segment's paths therefore stay in the segment for the whole batch (its
+// population only shrinks, so `seg_cap` = its bounce-0 share always suffices), fill counts are plain
+// shared-memory counters written back once per block, and no global atomic is issued anywhere.  (One global
+// counter per queue was the top stall of both extend and shade: ~2.5 same-sector atomics per warp iteration.)
 struct PathState {
     float4* ray_o;     // [cap] origin.xyz
     float4* ray_d;     // [cap] direction.xyz (never normalised: ray.rs)
@@ -25,12 +34,18 @@ struct PathState {
     float4* win_b;     // [cap] triangle barycentrics b0, b1, b2 (written for mesh hits only); .w = rank between passes
     float4* atten;     // [FW_MAX_DEPTH][cap] attenuation chain (see fold_radiance)
     float4* radiance;  // [cap] finished path radiance
-    uint32_t* q_extend[2];             // ping-pong extend queues
+    uint32_t* q_extend[2];             // ping-pong extend queues   (all queues: [nseg][seg_cap] path ids)
     uint32_t* q_mesh;                  // paths whose ray still has to walk a mesh (two-pass extend)
     uint32_t* q_mat[MAT_NUM_QUEUES];   // per-material shade queues
-    uint32_t* counters;                // [FW_MAX_DEPTH + 2][FW_COUNTERS_PER_BOUNCE]
+    uint32_t* counters;                // [FW_MAX_DEPTH + 2][FW_NUM_QUEUES][nseg] fill counts
     uint32_t cap;
+    uint32_t nseg, seg_cap;
 };
+// Counter rows: material / mesh queues of bounce b live in row b; the extend queue CONSUMED at bounce b lives in
+// row b (raygen fills row 0, the shade kernels of bounce b fill row b + 1).
+FW_DEV uint32_t* counter_row(const PathState& ps, uint32_t row, int queue) {
+    return ps.counters + ((size_t)row * FW_NUM_QUEUES + queue) * ps.nseg;
+}
 
 struct Batch {
     uint32_t pix0, npix, s0, ns;
@@ -62,9 +77,17 @@ FW_DEV void primary_ray(const CameraRec& cam, uint32_t width, uint32_t height, u
     d = ll + u * hor + v * ver - pos - offset;
 }
 
-__global__ void __launch_bounds__(256) raygen_kernel(CameraRec cam, Batch b, uint2 seed, PathState ps) {
-    uint32_t total = b.npix * b.ns;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+// One block per segment.  Tile t (FW_TILE consecutive paths) belongs to segment t % nseg, so every segment gets an
+// even mix of the image; entry e of segment `seg` is path ((e / TILE) * nseg + seg) * TILE + e % TILE.  Besides
+// the rays, raygen writes the segment's bounce-0 extend queue, so that extend has one input form on every bounce.
+__global__ void __launch_bounds__(FW_BLOCK) raygen_kernel(CameraRec cam, Batch b, uint2 seed, PathState ps) {
+    const uint32_t total = b.npix * b.ns;
+    const uint32_t seg = blockIdx.x;
+    uint32_t* q = ps.q_extend[0] + (size_t)seg * ps.seg_cap;
+    uint32_t count = 0;
+    for (uint32_t e = threadIdx.x; e < ps.seg_cap; e += FW_BLOCK) {
+        uint32_t p = ((e / FW_TILE) * ps.nseg + seg) * FW_TILE + (e % FW_TILE);
+        if (p >= total) break;   // p grows with e: the valid entries are a prefix
         uint32_t pixel, sample;
         batch_path(b, p, pixel, sample);
         float3 o, d;
@@ -72,12 +95,37 @@ __global__ void __launch_bounds__(256) raygen_kernel(CameraRec cam, Batch b, uin
         ps.ray_o[p] = make_float4(o.x, o.y, o.z, 0.0f);
         ps.ray_d[p] = make_float4(d.x, d.y, d.z, 0.0f);
         ps.radiance[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        q[e] = p;
+        count = e + 1;
     }
+    // the segment's entry count = 1 + the largest valid e over the block
+    __shared__ uint32_t s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    if (count) atomicMax(&s_count, count);
+    __syncthreads();
+    if (threadIdx.x == 0) counter_row(ps, 0, 6)[seg] = s_count;
 }
 
-// Append `path` to queue `k` for every lane whose `mine` == k: one atomicAdd per warp per non-empty queue.
+// ---- segment plumbing ------------------------------------------------------------------------------------
+// Every queue-driven kernel runs one block per segment (gridDim.x == nseg).  Fill counters of the block's segment
+// live in shared memory while the block runs.  `open` continues from the counts already in global memory: earlier
+// kernels of the same bounce append to the same regions (the shade kernels share the next extend queue, pass 2
+// continues pass 1's material queues); rows nobody wrote yet hold the zeros of the per-batch memset.
 template <int NQ>
-FW_DEV void warp_enqueue(uint32_t* const* queues, uint32_t* counters, int mine, uint32_t path) {
+FW_DEV void seg_open(uint32_t* s_fill, const PathState& ps, const uint32_t* counter_rows /* [NQ][nseg] */, uint32_t seg) {
+    if (threadIdx.x < NQ) s_fill[threadIdx.x] = counter_rows[(size_t)threadIdx.x * ps.nseg + seg];
+    __syncthreads();
+}
+template <int NQ>
+FW_DEV void seg_close(const uint32_t* s_fill, const PathState& ps, uint32_t* counter_rows, uint32_t seg) {
+    __syncthreads();
+    if (threadIdx.x < NQ) counter_rows[(size_t)threadIdx.x * ps.nseg + seg] = s_fill[threadIdx.x];
+}
+// Append `path` to queue `k` of the segment for every lane whose `mine` == k: one shared-memory atomic per warp per
+// non-empty queue reserves the slots (warp ballot / popc compaction).  All 32 lanes must call.
+template <int NQ>
+FW_DEV void seg_enqueue(uint32_t* const* queues, uint32_t* s_fill, uint32_t seg_base, int mine, uint32_t path) {
     unsigned lane = threadIdx.x & 31u;
     unsigned lt = (1u << lane) - 1u;
 #pragma unroll
@@ -86,16 +134,15 @@ FW_DEV void warp_enqueue(uint32_t* const* queues, uint32_t* counters, int mine, 
         if (mask == 0u) continue;
         int leader = __ffs(mask) - 1;
         uint32_t base = 0;
-        if ((int)lane == leader) base = atomicAdd(&counters[k], (uint32_t)__popc(mask));
+        if ((int)lane == leader) base = atomicAdd(&s_fill[k], (uint32_t)__popc(mask));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (mine == k) queues[k][base + __popc(mask & lt)] = path;
+        if (mine == k) queues[k][seg_base + base + __popc(mask & lt)] = path;
     }
 }
 
 // extend: closest hit for every queued path; writes the winning (t, object, primitive, barycentrics) and
 // sorts the path into its material's shade queue (or the miss queue).  The full hit record is rebuilt by the
 // shade kernel that consumes it (finalize_hit), so it never travels through HBM.
-constexpr int FW_REFILL_LANES = 22;
 
 // Publishes a ray's result and returns the shade queue it belongs to.  The material index travels with the
 // record so that the shade kernel can fetch its material in parallel with the object records.
@@ -130,170 +177,84 @@ FW_DEV void load_winner_bary(const DeviceScene& S, const PathState& ps, uint32_t
     }
 }
 
-// Persistent variant for incoherent bounces: each warp reserves FW_CHUNK_RAYS queue entries at a time (one
-// atomicAdd per chunk) and hands them to lanes as they free up; a finished lane just stores its winner record
-// (classification into material queues is a separate, fully converged pass: classify_kernel).  The traversal
-// burst ends when fewer than `refill_lanes` lanes are still walking, as long as there is work left to hand out.
-constexpr int FW_CHUNK_RAYS = 128;
-template <bool NESTED, bool MESHES>
-__global__ void __launch_bounds__(128) extend_bvh_persistent_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
-                                                                    const uint32_t* __restrict__ q_in,
-                                                                    const uint32_t* __restrict__ count_in, uint32_t n_direct,
-                                                                    uint32_t* counters_out, int refill_lanes) {
-    const uint32_t total = count_in ? *count_in : n_direct;
-    uint32_t* cursor = counters_out + 7;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt = (1u << lane) - 1u;
-    bool active = false;
-    uint32_t path = 0;
-    uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
-    bool more = true;                        // warp-uniform: the global queue may still have entries
-    RngKey key{seed, 0u, 0u, bounce};
-    UnifiedWalker<false, NESTED, MESHES> wk;
-    int stack_code[FW_STACK];
-    float stack_te[FW_STACK];
-    for (;;) {
-        unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle) {
-            if (chunk_next >= chunk_end && more) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(cursor, (uint32_t)FW_CHUNK_RAYS);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                chunk_next = base;
-                chunk_end = min(base + (uint32_t)FW_CHUNK_RAYS, total);
-                if (base >= total) { more = false; chunk_next = chunk_end = 0; }
-            }
-            if (chunk_next < chunk_end) {
-                uint32_t i = chunk_next + __popc(idle & lt);
-                if (!active && i < chunk_end) {
-                    path = q_in ? q_in[i] : i;
-                    float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
-                    batch_path(b, path, key.pixel, key.sample);
-                    if (wk.init(S, o, d, stack_code, stack_te, nullptr)) active = true;
-                    else store_winner(S, ps, path, wk.w);
-                }
-                chunk_next = min(chunk_next + (uint32_t)__popc(idle), chunk_end);
-            }
-        }
-        unsigned act = __ballot_sync(0xffffffffu, active);
-        bool can_refill = more || chunk_next < chunk_end;
-        if (act == 0u) {
-            if (can_refill) continue;
-            break;
-        }
-        int keep = can_refill ? min(__popc(act), refill_lanes) : 1;
-        do {
-            if (active) {
-                if (!wk.step(S, key, nullptr)) {
-                    store_winner(S, ps, path, wk.w);
-                    active = false;
-                }
-            }
-        } while (__popc(__ballot_sync(0xffffffffu, active)) >= keep);
-    }
-}
-
-// Sorts the paths of an extend queue into the per-material shade queues from their winner records (used after
-// extend_bvh_persistent_kernel; the grid-stride extend kernels do this themselves).
-__global__ void __launch_bounds__(256) classify_kernel(DeviceScene S, PathState ps, const uint32_t* __restrict__ q_in,
-                                                       const uint32_t* __restrict__ count_in, uint32_t n_direct,
-                                                       uint32_t* counters_out) {
-    uint32_t total = count_in ? *count_in : n_direct;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
-        uint32_t i = base + threadIdx.x;
+// Common shape of the extend kernels: one block per segment, FW_BLOCK entries per iteration; `trace` maps
+// (path, o, d, key) to the shade queue of the path (after publishing the winner).
+#define FW_EXTEND_PROLOGUE(NQ_OUT)                                                                         \
+    __shared__ uint32_t s_fill[FW_NUM_QUEUES];                                                               \
+    const uint32_t in_count = counter_row(ps, bounce, FW_Q_EXTEND)[blockIdx.x];                              \
+    seg_open<NQ_OUT>(s_fill, ps, counter_row(ps, bounce, 0), blockIdx.x);                                    \
+    for (uint32_t e0 = 0; e0 < in_count; e0 += FW_BLOCK) {                                                   \
+        const bool valid = e0 + threadIdx.x < in_count;                                                      \
+        uint32_t path = 0;                                                                                   \
+        if (valid) path = ps.q_extend[bounce & 1][(size_t)blockIdx.x * ps.seg_cap + e0 + threadIdx.x];       \
         int mine = -1;
-        uint32_t path = 0;
-        if (i < total) {
-            path = q_in ? q_in[i] : i;
-            float4 a = ps.win_a[path];
-            int obj = __float_as_int(a.y);
-            mine = obj < 0 ? (int)MAT_MISS : __ldg(&S.mats[__float_as_int(a.w)].kind);
-        }
-        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
-    }
-}
+#define FW_EXTEND_EPILOGUE(NQ_OUT, QUEUES)                                                                 \
+        seg_enqueue<NQ_OUT>(QUEUES, s_fill, blockIdx.x * ps.seg_cap, mine, path);                            \
+    }                                                                                                        \
+    seg_close<NQ_OUT>(s_fill, ps, counter_row(ps, bounce, 0), blockIdx.x);
 
 // Debug twin of the BVH extend: also records the number of box tests each path needed (FW_DEBUG_STEPS=1).
-__global__ void __launch_bounds__(128) extend_bvh_debug_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
-                                                               const uint32_t* __restrict__ q_in,
-                                                               const uint32_t* __restrict__ count_in, uint32_t n_direct,
-                                                               uint32_t* counters_out, uint32_t* steps) {
-    uint32_t total = count_in ? *count_in : n_direct;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
-        uint32_t i = base + threadIdx.x;
-        int mine = -1;
-        uint32_t path = 0;
-        if (i < total) {
-            path = q_in ? q_in[i] : i;
-            float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
-            RngKey key{seed, 0u, 0u, bounce};
-            batch_path(b, path, key.pixel, key.sample);
-            Winner w;
-            Counters cnt{0, 0};
-            trace_unified<true, true>(S, o, d, key, w, &cnt);
-            steps[path] = (uint32_t)cnt.node_tests;
-            mine = store_winner(S, ps, path, w);
-        }
-        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
-    }
+__global__ void __launch_bounds__(FW_BLOCK) extend_bvh_debug_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                                    uint32_t* steps) {
+    FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
+            if (valid) {
+                float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
+                RngKey key{seed, 0u, 0u, bounce};
+                batch_path(b, path, key.pixel, key.sample);
+                Winner w;
+                Counters cnt{0, 0};
+                trace_unified<true, true>(S, o, d, key, w, &cnt);
+                steps[path] = (uint32_t)cnt.node_tests;
+                mine = store_winner(S, ps, path, w);
+            }
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES, ps.q_mat)
 }
 
 // Two-pass extend for BVH scenes with TriangleMesh objects (see UnifiedWalker PHASE).  Pass 1 settles every ray
 // against the non-mesh objects and the mesh root boxes; rays that must enter a mesh are compacted into q_mesh
-// (counter slot 7) and finished by pass 2, where every lane of a warp is doing real mesh traversal.
+// and finished by pass 2, where every lane of a warp is doing real mesh traversal.
 template <bool NESTED>
-__global__ void __launch_bounds__(128, FW_EXTEND_MIN_BLOCKS) extend_pass1_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
-                                                           const uint32_t* __restrict__ q_in,
-                                                           const uint32_t* __restrict__ count_in, uint32_t n_direct,
-                                                           uint32_t* counters_out) {
-    uint32_t total = count_in ? *count_in : n_direct;
-    uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t* q7[MAT_NUM_QUEUES + 2];
+__global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass1_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
+                                                                                uint32_t bounce) {
+    uint32_t* q8[FW_NUM_QUEUES];
 #pragma unroll
-    for (int k = 0; k < MAT_NUM_QUEUES; ++k) q7[k] = ps.q_mat[k];
-    q7[6] = nullptr;
-    q7[7] = ps.q_mesh;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
-        uint32_t i = base + threadIdx.x;
-        int mine = -1;
-        uint32_t path = 0;
-        if (i < total) {
-            path = q_in ? q_in[i] : i;
-            float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
-            RngKey key{seed, 0u, 0u, bounce};
-            batch_path(b, path, key.pixel, key.sample);
-            UnifiedWalker<false, NESTED, true, 1> wk;
-            int stack_code[FW_STACK];
-            float stack_te[FW_STACK];
-            if (wk.init(S, o, d, stack_code, stack_te, nullptr)) {
-                while (wk.step(S, key, nullptr)) {
+    for (int k = 0; k < MAT_NUM_QUEUES; ++k) q8[k] = ps.q_mat[k];
+    q8[FW_Q_EXTEND] = nullptr;   // never selected here (slot 6 of the counter rows belongs to the shade kernels)
+    q8[FW_Q_MESH] = ps.q_mesh;
+    FW_EXTEND_PROLOGUE(FW_NUM_QUEUES)
+            if (valid) {
+                float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
+                RngKey key{seed, 0u, 0u, bounce};
+                batch_path(b, path, key.pixel, key.sample);
+                UnifiedWalker<false, NESTED, true, 1> wk;
+                int stack_code[FW_STACK];
+                float stack_te[FW_STACK];
+                if (wk.init(S, o, d, stack_code, stack_te, nullptr)) {
+                    while (wk.step(S, key, nullptr)) {
+                    }
+                }
+                mine = store_winner(S, ps, path, wk.w);
+                if (wk.pending) {
+                    // pass 2 needs the rank of the pass-1 winner (a non-mesh object, so win_b is free)
+                    if (wk.w.found) ps.win_b[path] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(wk.w.rank));
+                    mine = FW_Q_MESH;
                 }
             }
-            mine = store_winner(S, ps, path, wk.w);
-            if (wk.pending) {
-                // pass 2 needs the rank of the pass-1 winner (a non-mesh object, so win_b is free)
-                if (wk.w.found) ps.win_b[path] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(wk.w.rank));
-                mine = 7;
-            }
-        }
-        // queue 6 is never selected (slot 6 of the counter row belongs to the shade kernels)
-        warp_enqueue<MAT_NUM_QUEUES + 2>(q7, counters_out, mine, path);
-    }
+    FW_EXTEND_EPILOGUE(FW_NUM_QUEUES, q8)
 }
 template <bool NESTED>
-__global__ void __launch_bounds__(128, FW_EXTEND_MIN_BLOCKS) extend_pass2_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
-                                                           uint32_t* counters_out) {
-    uint32_t total = counters_out[7];
-    const uint32_t* __restrict__ q_in = ps.q_mesh;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
-        uint32_t i = base + threadIdx.x;
-        int mine = -1;
+__global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass2_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
+                                                                                uint32_t bounce) {
+    __shared__ uint32_t s_fill[FW_NUM_QUEUES];
+    const uint32_t in_count = counter_row(ps, bounce, FW_Q_MESH)[blockIdx.x];
+    if (in_count == 0) return;  // block-uniform
+    seg_open<MAT_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), blockIdx.x);   // continues pass 1's material queues
+    for (uint32_t e0 = 0; e0 < in_count; e0 += FW_BLOCK) {
+        const bool valid = e0 + threadIdx.x < in_count;
         uint32_t path = 0;
-        if (i < total) {
-            path = q_in[i];
+        int mine = -1;
+        if (valid) {
+            path = ps.q_mesh[(size_t)blockIdx.x * ps.seg_cap + e0 + threadIdx.x];
             float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
             RngKey key{seed, 0u, 0u, bounce};
             batch_path(b, path, key.pixel, key.sample);
@@ -311,71 +272,64 @@ __global__ void __launch_bounds__(128, FW_EXTEND_MIN_BLOCKS) extend_pass2_kernel
             }
             mine = store_winner(S, ps, path, wk.w);
         }
-        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
+        seg_enqueue<MAT_NUM_QUEUES>(ps.q_mat, s_fill, blockIdx.x * ps.seg_cap, mine, path);
     }
+    seg_close<MAT_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), blockIdx.x);
 }
 
 template <bool NESTED, bool MESHES>
-__global__ void __launch_bounds__(128, FW_EXTEND_MIN_BLOCKS) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
-                                                                const uint32_t* __restrict__ q_in,
-                                                                const uint32_t* __restrict__ count_in, uint32_t n_direct,
-                                                                uint32_t* counters_out) {
-    uint32_t total = count_in ? *count_in : n_direct;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
-        uint32_t i = base + threadIdx.x;
-        int mine = -1;
-        uint32_t path = 0;
-        if (i < total) {
-            path = q_in ? q_in[i] : i;
-            float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
-            float3 o = f3(ro), d = f3(rd);
-            RngKey key{seed, 0u, 0u, bounce};
-            batch_path(b, path, key.pixel, key.sample);
-            Winner w;
-            trace_unified<false, NESTED, MESHES>(S, o, d, key, w, nullptr);
-            mine = store_winner(S, ps, path, w);
-        }
-        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
-    }
+__global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
+                                                                                     uint32_t bounce) {
+    FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
+            if (valid) {
+                float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
+                float3 o = f3(ro), d = f3(rd);
+                RngKey key{seed, 0u, 0u, bounce};
+                batch_path(b, path, key.pixel, key.sample);
+                Winner w;
+                trace_unified<false, NESTED, MESHES>(S, o, d, key, w, nullptr);
+                mine = store_winner(S, ps, path, w);
+            }
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES, ps.q_mat)
 }
 
 // Linear-scan scenes (Renderer.use_bvh == false, scene.rs:137-149): every ray tests every object in scene
-// order, so there is no traversal-length divergence to balance; a plain grid-stride loop.
+// order, so there is no traversal-length divergence to balance.
 // NESTED: the scene contains a TriangleMesh (its own BVH is walked inside the object test).
+// This object-loop form serves scenes whose LinProgram does not fit kernel-parameter space.
 template <bool NESTED>
-__global__ void __launch_bounds__(128) extend_linear_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
-                                                            const uint32_t* __restrict__ q_in,
-                                                            const uint32_t* __restrict__ count_in, uint32_t n_direct,
-                                                            uint32_t* counters_out) {
-    uint32_t total = count_in ? *count_in : n_direct;
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
-        uint32_t i = base + threadIdx.x;
-        int mine = -1;
-        uint32_t path = 0;
-        if (i < total) {
-            path = q_in ? q_in[i] : i;
-            float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
-            float3 o = f3(ro), d = f3(rd);
-            RngKey key{seed, 0u, 0u, bounce};
-            batch_path(b, path, key.pixel, key.sample);
-            Winner w;
-            w.found = false; w.t = 0.0f; w.obj = -1; w.rank = -1;
-            float closest = 2e9f;
-            if (nan_direction(d)) nan_direction_winner(S.nan_lin_obj, S.nan_lin_prim, w);
-            else
-            for (int obj = 0; obj < S.n_objects; ++obj) {
-                ObjHit h;
-                if (object_test<false, NESTED>(S, obj, o, d, 0.001f, closest, FW_FLT_MAX, key, h, nullptr)) {
-                    closest = h.t;
-                    w.found = true; w.t = h.t; w.obj = obj; w.rank = obj; w.h = h;
-                }
+__global__ void __launch_bounds__(FW_BLOCK) extend_linear_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce) {
+    FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
+            if (valid) {
+                float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
+                float3 o = f3(ro), d = f3(rd);
+                RngKey key{seed, 0u, 0u, bounce};
+                batch_path(b, path, key.pixel, key.sample);
+                Winner w;
+                trace_linear_scan<false, NESTED>(S, o, d, key, w, nullptr);
+                mine = store_winner(S, ps, path, w);
             }
-            mine = store_winner(S, ps, path, w);
-        }
-        warp_enqueue<MAT_NUM_QUEUES>(ps.q_mat, counters_out, mine, path);
-    }
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES, ps.q_mat)
+}
+
+// The same query driven by the scene's LinProgram in kernel-parameter space (intersect.cuh trace_linear_prog):
+// no per-lane loads of scene records, uniform item dispatch.  Every lane of a warp runs the program (lanes past
+// the end of the segment trace a dummy ray and drop the result) so that the PRETEST vote sees the whole warp.
+template <bool GENERIC, bool NESTED, bool PRETEST>
+__global__ void __launch_bounds__(FW_BLOCK) extend_linear_prog_kernel(const __grid_constant__ LinProgram P, DeviceScene S, PathState ps,
+                                                                      Batch b, uint2 seed, uint32_t bounce) {
+    FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
+            float3 o = f3(1e30f, 1e30f, 1e30f), d = f3(1.0f, 1.0f, 1.0f);
+            if (valid) {
+                float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
+                o = f3(ro); d = f3(rd);
+            }
+            RngKey key{seed, 0u, 0u, bounce};
+            if (GENERIC) batch_path(b, path, key.pixel, key.sample);
+            Winner w;
+            trace_linear_prog<false, GENERIC, NESTED, PRETEST>(P, S, o, d, key, w, nullptr);
+            if (valid) mine = store_winner(S, ps, path, w);
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES, ps.q_mat)
 }
 
 // render.rs:23 evaluated without recursion: colour = a0 * (a1 * (... (a_{k-1} * terminal))) with the same
@@ -391,95 +345,113 @@ FW_DEV float3 fold_radiance(const PathState& ps, uint32_t path, uint32_t bounce,
 }
 
 // render.rs:31 — environment lookup for rays that left the scene
-__global__ void __launch_bounds__(256) miss_kernel(DeviceScene S, PathState ps, uint32_t bounce,
-                                                   const uint32_t* __restrict__ counters) {
-    uint32_t total = counters[MAT_MISS];
-    const uint32_t* q = ps.q_mat[MAT_MISS];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        uint32_t path = q[i];
-        float3 env = environment_sample(S.env, f3(ps.ray_d[path]));
-        float3 c = fold_radiance(ps, path, bounce, env);
-        ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
+__global__ void __launch_bounds__(FW_BLOCK) miss_kernel(DeviceScene S, PathState ps, uint32_t bounce) {
+    {
+        const uint32_t total = counter_row(ps, bounce, MAT_MISS)[blockIdx.x];
+        const uint32_t* qs = ps.q_mat[MAT_MISS] + (size_t)blockIdx.x * ps.seg_cap;
+        for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
+            uint32_t path = qs[i];
+            float3 env = environment_sample(S.env, f3(ps.ray_d[path]));
+            float3 c = fold_radiance(ps, path, bounce, env);
+            ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
+        }
     }
 }
 
 // render.rs:20,25-28 with material.rs:174-180 — emissive surfaces end the path with their texture value
-__global__ void __launch_bounds__(256) shade_emissive_kernel(DeviceScene S, PathState ps, uint32_t bounce,
-                                                             const uint32_t* __restrict__ counters) {
-    uint32_t total = counters[MAT_EMISSIVE];
-    const uint32_t* q = ps.q_mat[MAT_EMISSIVE];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        uint32_t path = q[i];
-        int material;
-        Winner w = load_winner(ps, path, material);
-        load_winner_bary(S, ps, path, w);
-        HitRecord rec;
-        finalize_hit(S, w, f3(ps.ray_o[path]), f3(ps.ray_d[path]), rec, true);
-        int tex = __ldg(&S.mats[material].tex);
-        float3 emit = texture_sample(S, tex, rec.uv, rec.point);
-        float3 c = fold_radiance(ps, path, bounce, emit);
-        ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
+__global__ void __launch_bounds__(FW_BLOCK) shade_emissive_kernel(DeviceScene S, PathState ps, uint32_t bounce) {
+    {
+        const uint32_t total = counter_row(ps, bounce, MAT_EMISSIVE)[blockIdx.x];
+        const uint32_t* qs = ps.q_mat[MAT_EMISSIVE] + (size_t)blockIdx.x * ps.seg_cap;
+        for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
+            uint32_t path = qs[i];
+            int material;
+            Winner w = load_winner(ps, path, material);
+            load_winner_bary(S, ps, path, w);
+            HitRecord rec;
+            finalize_hit(S, w, f3(ps.ray_o[path]), f3(ps.ray_d[path]), rec, true);
+            int tex = __ldg(&S.mats[material].tex);
+            float3 emit = texture_sample(S, tex, rec.uv, rec.point);
+            float3 c = fold_radiance(ps, path, bounce, emit);
+            ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
+        }
     }
 }
 
 // Scattering materials: write the next ray + this vertex's attenuation, re-queue the path for extend.
 // Not launched for bounce == FW_MAX_DEPTH (render.rs:21: no scatter at depth 10; emit is zero).
+// The material kernels of one bounce run back to back and append to the same regions of the next extend queue.
 template <int MAT>
-__global__ void __launch_bounds__(256) shade_scatter_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
-                                                            uint32_t bounce, const uint32_t* __restrict__ counters_in,
-                                                            uint32_t* q_out, uint32_t* counters_out) {
-    uint32_t total = counters_in[MAT];
+__global__ void __launch_bounds__(FW_BLOCK) shade_scatter_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce) {
+    __shared__ uint32_t s_fill[1];
+    uint32_t* row_out = counter_row(ps, bounce + 1, FW_Q_EXTEND);
     const uint32_t* q = ps.q_mat[MAT];
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
-        uint32_t i = base + threadIdx.x;
-        int mine = -1;
-        uint32_t path = 0;
-        if (i < total) {
-            path = q[i];
-            float3 in_o = f3(ps.ray_o[path]), in_d = f3(ps.ray_d[path]);
-            int material;
-            Winner w = load_winner(ps, path, material);
-            const float4* mq = reinterpret_cast<const float4*>(&S.mats[material]);
-            float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);  // (kind, tex, param, needs_uv), (albedo, -)
-            load_winner_bary(S, ps, path, w);
-            HitRecord rec;
-            finalize_hit(S, w, in_o, in_d, rec, __float_as_int(m0.w) != 0);
-            float3 point = rec.point, normal = rec.normal;
-            uint32_t pixel, sample;
-            batch_path(b, path, pixel, sample);
-            RngKey key{seed, pixel, sample, bounce};
-            PhiloxStream rng(key, STREAM_SCATTER);
-            ScatterOut out;
-            if (MAT == MAT_LAMBERTIAN) {
-                scatter_lambertian(S, __float_as_int(m0.y), point, normal, rec.uv, rng, out);
-            } else if (MAT == MAT_METAL) {
-                scatter_metal(f3(m1), m0.z, in_d, point, normal, rng, out);
-            } else if (MAT == MAT_DIELECTRIC) {
-                scatter_dielectric(m0.z, in_d, point, normal, rng, out);
-            } else {
-                scatter_isotropic(S, __float_as_int(m0.y), point, rec.uv, rng, out);
+    uint32_t* q_out = ps.q_extend[(bounce + 1) & 1];
+    {
+        const uint32_t seg = blockIdx.x;
+        const uint32_t total = counter_row(ps, bounce, MAT)[seg];
+        if (total == 0) return;  // block-uniform
+        const uint32_t base = seg * ps.seg_cap;
+        seg_open<1>(s_fill, ps, row_out, seg);
+        for (uint32_t e0 = 0; e0 < total; e0 += FW_BLOCK) {
+            uint32_t i = e0 + threadIdx.x;
+            int mine = -1;
+            uint32_t path = 0;
+            if (i < total) {
+                path = q[base + i];
+                float3 in_o = f3(ps.ray_o[path]), in_d = f3(ps.ray_d[path]);
+                int material;
+                Winner w = load_winner(ps, path, material);
+                const float4* mq = reinterpret_cast<const float4*>(&S.mats[material]);
+                float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);  // (kind, tex, param, needs_uv), (albedo, -)
+                load_winner_bary(S, ps, path, w);
+                HitRecord rec;
+                finalize_hit(S, w, in_o, in_d, rec, __float_as_int(m0.w) != 0);
+                float3 point = rec.point, normal = rec.normal;
+                uint32_t pixel, sample;
+                batch_path(b, path, pixel, sample);
+                RngKey key{seed, pixel, sample, bounce};
+                PhiloxStream rng(key, STREAM_SCATTER);
+                ScatterOut out;
+                if (MAT == MAT_LAMBERTIAN) {
+                    scatter_lambertian(S, __float_as_int(m0.y), point, normal, rec.uv, rng, out);
+                } else if (MAT == MAT_METAL) {
+                    scatter_metal(f3(m1), m0.z, in_d, point, normal, rng, out);
+                } else if (MAT == MAT_DIELECTRIC) {
+                    scatter_dielectric(m0.z, in_d, point, normal, rng, out);
+                } else {
+                    scatter_isotropic(S, __float_as_int(m0.y), point, rec.uv, rng, out);
+                }
+                if (out.scattered) {
+                    ps.ray_o[path] = make_float4(out.origin.x, out.origin.y, out.origin.z, 0.0f);
+                    ps.ray_d[path] = make_float4(out.dir.x, out.dir.y, out.dir.z, 0.0f);
+                    ps.atten[(size_t)bounce * ps.cap + path] =
+                        make_float4(out.attenuation.x, out.attenuation.y, out.attenuation.z, 0.0f);
+                    mine = 0;
+                }
+                // absorbed (metal below the surface): radiance stays 0 (render.rs:25)
             }
-            if (out.scattered) {
-                ps.ray_o[path] = make_float4(out.origin.x, out.origin.y, out.origin.z, 0.0f);
-                ps.ray_d[path] = make_float4(out.dir.x, out.dir.y, out.dir.z, 0.0f);
-                ps.atten[(size_t)bounce * ps.cap + path] =
-                    make_float4(out.attenuation.x, out.attenuation.y, out.attenuation.z, 0.0f);
-                mine = 0;
-            }
-            // absorbed (metal below the surface): radiance stays 0 (render.rs:25)
+            seg_enqueue<1>(&q_out, s_fill, base, mine, path);
         }
-        warp_enqueue<1>(&q_out, counters_out + 6, mine, path);
+        seg_close<1>(s_fill, ps, row_out, seg);
     }
 }
 
-// Ray statistics without a host round trip per batch: rays traced = paths generated + every re-queued path.
-__global__ void tally_kernel(const uint32_t* __restrict__ counters, uint32_t n_paths, unsigned long long* total_rays) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long r = n_paths;
-        for (int bn = 0; bn < FW_MAX_DEPTH; ++bn) r += counters[bn * FW_COUNTERS_PER_BOUNCE + 6];
-        *total_rays += r;
+// Ray statistics without a host round trip per batch: rays traced = every entry of every bounce's extend queue.
+__global__ void __launch_bounds__(256) tally_kernel(PathState ps, unsigned long long* total_rays) {
+    __shared__ unsigned long long s_part[256];
+    unsigned long long r = 0;
+    for (int bn = 0; bn <= FW_MAX_DEPTH; ++bn) {   // row b = rays traced at bounce b (row 0 = the primary rays)
+        const uint32_t* row = counter_row(ps, bn, FW_Q_EXTEND);
+        for (uint32_t i = threadIdx.x; i < ps.nseg; i += 256) r += row[i];
     }
+    s_part[threadIdx.x] = r;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) s_part[threadIdx.x] += s_part[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_rays += s_part[0];
 }
 
 // render.rs:177-182 `total_color += color(...)`: samples of a pixel are added in sample order, so the fp32
@@ -543,6 +515,36 @@ __global__ void first_hit_probe(DeviceScene S, uint2 seed, uint32_t n, const flo
         RngKey key{seed, pixel ? pixel[i] : i, sample ? sample[i] : 0u, bounce ? bounce[i] : 0u};
         HitRecord rec;
         if (scene_closest_hit<USE_BVH, true>(S, o, d, key, rec, &cnt)) {
+            out.obj[i] = rec.obj; out.prim[i] = rec.prim; out.material[i] = rec.material; out.t[i] = rec.t;
+            out.point[3 * i] = rec.point.x; out.point[3 * i + 1] = rec.point.y; out.point[3 * i + 2] = rec.point.z;
+            out.normal[3 * i] = rec.normal.x; out.normal[3 * i + 1] = rec.normal.y; out.normal[3 * i + 2] = rec.normal.z;
+            out.uv[2 * i] = rec.uv.x; out.uv[2 * i + 1] = rec.uv.y;
+        } else {
+            out.obj[i] = -1; out.prim[i] = 0; out.material[i] = -1; out.t[i] = 0.0f;
+            out.point[3 * i] = out.point[3 * i + 1] = out.point[3 * i + 2] = 0.0f;
+            out.normal[3 * i] = out.normal[3 * i + 1] = out.normal[3 * i + 2] = 0.0f;
+            out.uv[2 * i] = out.uv[2 * i + 1] = 0.0f;
+        }
+    }
+    atomicAdd(&out.counters[0], cnt.node_tests);
+    atomicAdd(&out.counters[1], cnt.prim_tests);
+}
+
+// first-hit probe through the LinProgram path (what linear-scan renders execute)
+template <bool GENERIC>
+__global__ void first_hit_prog_probe(const __grid_constant__ LinProgram P, DeviceScene S, uint2 seed, uint32_t n, const float* origins,
+                                     const float* dirs, const uint32_t* pixel, const uint32_t* sample, const uint32_t* bounce,
+                                     FirstHitOut out) {
+    Counters cnt{0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float3 o = f3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        float3 d = f3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        RngKey key{seed, pixel ? pixel[i] : i, sample ? sample[i] : 0u, bounce ? bounce[i] : 0u};
+        Winner w;
+        trace_linear_prog<true, GENERIC, true, false>(P, S, o, d, key, w, &cnt);
+        if (w.found) {
+            HitRecord rec;
+            finalize_hit(S, w, o, d, rec);
             out.obj[i] = rec.obj; out.prim[i] = rec.prim; out.material[i] = rec.material; out.t[i] = rec.t;
             out.point[3 * i] = rec.point.x; out.point[3 * i + 1] = rec.point.y; out.point[3 * i + 2] = rec.point.z;
             out.normal[3 * i] = rec.normal.x; out.normal[3 * i + 1] = rec.normal.y; out.normal[3 * i + 2] = rec.normal.z;

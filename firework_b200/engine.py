@@ -91,6 +91,13 @@ class NativeScene:
         N.check(N.lib().fw_scene_mesh_leaf_order(self._h, obj, N.ptr(out), n))
         return out
 
+    def linear_program(self):
+        """The scene's linear-scan program as an (n_words, 4) float32 array (fw_types.h LinItem encoding)."""
+        n = N.check(N.lib().fw_scene_linear_program(self._h, None, 0))
+        out = np.zeros((n, 4), np.float32)
+        N.check(N.lib().fw_scene_linear_program(self._h, N.ptr(out), n))
+        return out
+
     def material_texture(self, material):
         return N.lib().fw_material_texture(self._h, material)
 

@@ -89,6 +89,10 @@ int fw_scene_top_leaf_order(const fw_scene* scene, int* out, int capacity);     
 int fw_scene_object_aabb(const fw_scene* scene, int object, float out_min_max[6]);   /* scene.rs:167-212 */
 int fw_scene_mesh_leaf_order(const fw_scene* scene, int object, int* out, int capacity); /* triangle ids */
 uint64_t fw_scene_device_bytes(const fw_scene* scene);  /* host->device bytes copied by fw_scene_commit */
+/* The linear-scan program of the scene (SceneInternal::hit, src/scene.rs:137-149, compiled to 16-byte words;
+ * encoding in firework_b200/csrc/fw_types.h LinItem).  Copies up to `capacity_words` words (4 floats each) and
+ * returns the program's length in words. */
+int fw_scene_linear_program(const fw_scene* scene, float* out_words, int capacity_words);
 
 /* ---- the hot path -------------------------------------------------------------------------------------
  * replaces: the per-pixel loop of Renderer::render (src/render.rs:123-196).
