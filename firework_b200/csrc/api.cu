@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -70,6 +71,7 @@ struct fw_scene {
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> texobjs;
     bool mat_present[MAT_NUM_QUEUES] = {false, false, false, false, false, false};
+    bool miss_is_zero = false;  // every escaping path contributes exactly 0: the miss kernel is not launched
     RenderCtx* ctx = nullptr;  // render-time state, borrowed from the per-device cache at commit
     size_t batch_paths = 0;    // 0 = default
     bool profiling = false;
@@ -350,6 +352,22 @@ int fw_scene_commit(fw_scene* sc, int device) {
     D.nan_bvh_obj = F.nan_bvh_obj; D.nan_bvh_prim = F.nan_bvh_prim;
     D.nan_lin_obj = F.nan_lin_obj; D.nan_lin_prim = F.nan_lin_prim;
     for (const MatRec& m : F.mats) sc->mat_present[m.kind] = true;
+    {
+        // render.rs:31 with a black ColorEnv: an escaping path returns attenuation-chain * 0.  That is exactly 0
+        // (radiance is pre-zeroed by raygen; adding +-0 never changes a sum that started at +0) as long as no
+        // attenuation can be NaN / inf: all texture values are scene constants or u8 texels (procedural noise is
+        // excluded because a NaN hit point would make it NaN), of magnitude <= 1e3 so ten factors cannot overflow.
+        bool ok = sc->desc.env_kind == ENV_COLOR && sc->desc.env_a[0] == 0.0f && sc->desc.env_a[1] == 0.0f && sc->desc.env_a[2] == 0.0f;
+        auto small = [](float v) { return std::fabs(v) <= 1e3f; };   // false for NaN
+        for (const TexRec& t : F.texs) {
+            if (t.kind == TEX_PERLIN || t.kind == TEX_TURBULENCE || t.kind == TEX_MARBLE) ok = false;
+            if (t.kind == TEX_CONSTANT && !(small(t.color[0]) && small(t.color[1]) && small(t.color[2]))) ok = false;
+        }
+        for (const MatRec& m : F.mats)
+            if (m.kind == MAT_METAL && !(small(m.albedo[0]) && small(m.albedo[1]) && small(m.albedo[2]))) ok = false;
+        if (const char* e = getenv("FW_SKIP_ZERO_MISS")) ok = ok && atoi(e) != 0;
+        sc->miss_is_zero = ok;
+    }
     sc->lin_prog_ok = F.lin_words.size() <= (size_t)FW_LIN_MAX_WORDS;
     if (const char* e = getenv("FW_LINEAR_PROGRAM")) sc->lin_prog_ok = sc->lin_prog_ok && atoi(e) != 0;
     memset(&sc->lin_prog, 0, sizeof(sc->lin_prog));
@@ -614,8 +632,10 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
         }
         tot.launches++;
         tot.extend_launches++;
-        miss_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, bounce);
-        tot.launches++;
+        if (!sc->miss_is_zero) {
+            miss_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, bounce);
+            tot.launches++;
+        }
         if (sc->mat_present[MAT_EMISSIVE]) {
             shade_emissive_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, bounce);
             tot.launches++;

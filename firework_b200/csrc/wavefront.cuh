@@ -12,6 +12,9 @@
 
 namespace fw {
 
+#ifndef FW_SHADE_MIN_BLOCKS
+#define FW_SHADE_MIN_BLOCKS 8    // shade kernels wait on dependent loads: cap registers at 64 (10 blocks = 51 regs spills: measured slower)
+#endif
 #ifndef FW_EXTEND_MIN_BLOCKS
 #define FW_EXTEND_MIN_BLOCKS 8   // __launch_bounds__ min blocks / SM of the BVH extend kernels (register cap knob)
 #endif
@@ -336,11 +339,15 @@ __global__ void __launch_bounds__(FW_BLOCK) extend_linear_prog_kernel(const __gr
 // right-nested association as `emit + attenuation * color(...)`; emit is zero at every scattering vertex
 // (material.rs:13-15), so the chain of attenuations is all that is needed.
 FW_DEV float3 fold_radiance(const PathState& ps, uint32_t path, uint32_t bounce, float3 terminal) {
+    // all loads first (independent, one HBM round trip), then the multiplications in the reference's order
+    float4 a[FW_MAX_DEPTH];
+#pragma unroll
+    for (int k = 0; k < FW_MAX_DEPTH; ++k)
+        if (k < (int)bounce) a[k] = ps.atten[(size_t)k * ps.cap + path];
     float3 x = terminal;
-    for (int k = (int)bounce - 1; k >= 0; --k) {
-        float4 a = ps.atten[(size_t)k * ps.cap + path];
-        x = f3(a.x, a.y, a.z) * x;
-    }
+#pragma unroll
+    for (int k = FW_MAX_DEPTH - 1; k >= 0; --k)
+        if (k < (int)bounce) x = f3(a[k].x, a[k].y, a[k].z) * x;
     return x;
 }
 
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(FW_BLOCK) shade_emissive_kernel(DeviceScene S,
 // Not launched for bounce == FW_MAX_DEPTH (render.rs:21: no scatter at depth 10; emit is zero).
 // The material kernels of one bounce run back to back and append to the same regions of the next extend queue.
 template <int MAT>
-__global__ void __launch_bounds__(FW_BLOCK) shade_scatter_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce) {
+__global__ void __launch_bounds__(FW_BLOCK, FW_SHADE_MIN_BLOCKS) shade_scatter_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce) {
     __shared__ uint32_t s_fill[1];
     uint32_t* row_out = counter_row(ps, bounce + 1, FW_Q_EXTEND);
     const uint32_t* q = ps.q_mat[MAT];
