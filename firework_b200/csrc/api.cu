@@ -90,13 +90,17 @@ static int upload(fw_scene* sc, const std::vector<T>& host, const T** dev) {
     return FW_OK;
 }
 
+static void free_path_state(PathState& ps) {
+    auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
+    for (int i = 0; i < 2; ++i) { fr(ps.xo[i]); fr(ps.xd[i]); }
+    for (HitQueue& q : ps.hq) { fr(q.o); fr(q.d); fr(q.w); fr(q.b); }
+    fr(ps.atten); fr(ps.radiance); fr(ps.counters);
+}
 static void destroy_ctx(RenderCtx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
-    fr(c->ps.ray_o); fr(c->ps.ray_d); fr(c->ps.win_a); fr(c->ps.win_b); fr(c->ps.atten);
-    fr(c->ps.radiance); fr(c->ps.q_extend[0]); fr(c->ps.q_extend[1]); fr(c->ps.q_mesh); fr(c->ps.counters);
-    for (int k = 0; k < MAT_NUM_QUEUES; ++k) fr(c->ps.q_mat[k]);
+    free_path_state(c->ps);
     fr(c->d_sum); fr(c->d_rgb);
     if (c->h_rays) cudaFreeHost(c->h_rays);
     if (c->d_rays) cudaFree(c->d_rays);
@@ -462,32 +466,42 @@ static void segment_geometry(const fw_scene* sc, size_t n, uint32_t* nseg, uint3
     *seg_cap = (uint32_t)(((tiles + want - 1) / want) * FW_TILE);
 }
 
+// Path-state streams for batches of up to `cap` paths.  Only the shade queues of materials present in the scene
+// (and the mesh queue / barycentric streams when it has TriangleMesh objects) are allocated; a cached context
+// grows on demand when a later scene needs more.
 static int ensure_path_state(fw_scene* sc, size_t cap) {
     RenderCtx* ctx = sc->ctx;
     const size_t nseg_max = (size_t)sc->sm_count * FW_SEG_PER_SM_MAX;
-    if (ctx->ps_cap >= cap && ctx->ps_nseg_max >= nseg_max) {
-        ctx->ps.cap = (uint32_t)ctx->ps_cap;
-        return FW_OK;
-    }
-    auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     PathState& ps = ctx->ps;
-    fr(ps.ray_o); fr(ps.ray_d); fr(ps.win_a); fr(ps.win_b); fr(ps.atten); fr(ps.radiance);
-    fr(ps.q_extend[0]); fr(ps.q_extend[1]); fr(ps.q_mesh); fr(ps.counters);
-    for (int k = 0; k < MAT_NUM_QUEUES; ++k) fr(ps.q_mat[k]);
-    ctx->ps_cap = 0;
+    if (ctx->ps_cap < cap || ctx->ps_nseg_max < nseg_max) {
+        free_path_state(ps);
+        ctx->ps_cap = 0;
+    }
+    cap = std::max(cap, ctx->ps_cap);   // streams added later for another scene get the context's full size
     // queue regions: nseg * seg_cap <= n + nseg * FW_TILE slots for any batch of n <= cap paths
     const size_t qcap = cap + (nseg_max + 1) * FW_TILE;
-    FW_CUDA(cudaMalloc(&ps.ray_o, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.ray_d, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.win_a, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.win_b, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.atten, cap * sizeof(float4) * FW_MAX_DEPTH));
-    FW_CUDA(cudaMalloc(&ps.radiance, cap * sizeof(float4)));
-    FW_CUDA(cudaMalloc(&ps.q_extend[0], qcap * sizeof(uint32_t)));
-    FW_CUDA(cudaMalloc(&ps.q_extend[1], qcap * sizeof(uint32_t)));
-    FW_CUDA(cudaMalloc(&ps.q_mesh, qcap * sizeof(uint32_t)));
-    for (int k = 0; k < MAT_NUM_QUEUES; ++k) FW_CUDA(cudaMalloc(&ps.q_mat[k], qcap * sizeof(uint32_t)));
-    FW_CUDA(cudaMalloc(&ps.counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * nseg_max));
+    auto need = [&](float4*& p, size_t n) -> int {
+        if (p) return FW_OK;
+        FW_CUDA(cudaMalloc(&p, n * sizeof(float4)));
+        return FW_OK;
+    };
+    int rc;
+#define NEED(ptr, n) if ((rc = need(ptr, n)) != FW_OK) return rc
+    for (int i = 0; i < 2; ++i) { NEED(ps.xo[i], qcap); NEED(ps.xd[i], qcap); }
+    NEED(ps.atten, cap * FW_MAX_DEPTH);
+    NEED(ps.radiance, cap);
+    const bool mesh = sc->flat.has_mesh;
+    for (int k = 0; k < FW_NUM_QUEUES; ++k) {
+        bool used = k == MAT_MISS || (k < MAT_NUM_QUEUES && sc->mat_present[k]) || (k == FW_Q_MESH && sc->flat.has_top_mesh);
+        if (!used) continue;
+        NEED(ps.hq[k].d, qcap);
+        if (k == MAT_MISS) continue;
+        NEED(ps.hq[k].o, qcap);
+        NEED(ps.hq[k].w, qcap);
+        if (mesh) NEED(ps.hq[k].b, qcap);
+    }
+#undef NEED
+    if (!ps.counters) FW_CUDA(cudaMalloc(&ps.counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * nseg_max));
     ps.cap = (uint32_t)cap;
     ctx->ps_cap = cap;
     ctx->ps_nseg_max = nseg_max;
@@ -556,35 +570,37 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
                 sum += hs[i];
                 if (!any || hs[i] > hs[worst]) { worst = i; any = true; }
             }
-            float4 ro, rd;
-            FW_CUDA(cudaMemcpy(&ro, ps.ray_o + worst, 16, cudaMemcpyDeviceToHost));
-            FW_CUDA(cudaMemcpy(&rd, ps.ray_d + worst, 16, cudaMemcpyDeviceToHost));
+            // the segments' extend-queue records of this bounce: (o, path), (d, -)
+            std::vector<float4> qo, qd;
+            {
+                std::vector<uint32_t> cnts(ps.nseg);
+                FW_CUDA(cudaMemcpy(cnts.data(), ps.counters + ((size_t)bounce * FW_NUM_QUEUES + FW_Q_EXTEND) * ps.nseg,
+                                   (size_t)ps.nseg * 4, cudaMemcpyDeviceToHost));
+                for (uint32_t seg = 0; seg < ps.nseg; ++seg) {
+                    if (!cnts[seg]) continue;
+                    size_t at = qo.size();
+                    qo.resize(at + cnts[seg]); qd.resize(at + cnts[seg]);
+                    FW_CUDA(cudaMemcpy(qo.data() + at, ps.xo[bounce & 1] + (size_t)seg * ps.seg_cap, (size_t)cnts[seg] * 16, cudaMemcpyDeviceToHost));
+                    FW_CUDA(cudaMemcpy(qd.data() + at, ps.xd[bounce & 1] + (size_t)seg * ps.seg_cap, (size_t)cnts[seg] * 16, cudaMemcpyDeviceToHost));
+                }
+            }
+            float4 ro = make_float4(0, 0, 0, 0), rd = ro;
+            for (size_t i = 0; i < qo.size(); ++i) {
+                uint32_t pth;
+                memcpy(&pth, &qo[i].w, 4);
+                if (pth == worst) { ro = qo[i]; rd = qd[i]; }
+            }
             if (const char* dump = getenv("FW_DEBUG_DUMP")) {
                 // per-bounce dump for offline coherence analysis: queue order, per-path box tests, rays
-                std::vector<uint32_t> hq;
-                {
-                    std::vector<uint32_t> cnts(ps.nseg);
-                    FW_CUDA(cudaMemcpy(cnts.data(), ps.counters + ((size_t)bounce * FW_NUM_QUEUES + FW_Q_EXTEND) * ps.nseg,
-                                       (size_t)ps.nseg * 4, cudaMemcpyDeviceToHost));
-                    std::vector<uint32_t> region(ps.seg_cap);
-                    for (uint32_t seg = 0; seg < ps.nseg; ++seg) {
-                        if (!cnts[seg]) continue;
-                        FW_CUDA(cudaMemcpy(region.data(), ps.q_extend[bounce & 1] + (size_t)seg * ps.seg_cap, (size_t)cnts[seg] * 4,
-                                           cudaMemcpyDeviceToHost));
-                        hq.insert(hq.end(), region.begin(), region.begin() + cnts[seg]);
-                    }
-                }
-                uint32_t cnt = (uint32_t)hq.size();
-                std::vector<float4> ho(N), hd(N);
-                FW_CUDA(cudaMemcpy(ho.data(), ps.ray_o, (size_t)N * 16, cudaMemcpyDeviceToHost));
-                FW_CUDA(cudaMemcpy(hd.data(), ps.ray_d, (size_t)N * 16, cudaMemcpyDeviceToHost));
+                uint32_t cnt = (uint32_t)qo.size();
                 std::string fn = std::string(dump) + "_b" + std::to_string(bounce) + ".bin";
                 FILE* f = fopen(fn.c_str(), "wb");
                 if (f) {
                     fwrite(&cnt, 4, 1, f);
                     for (uint32_t i = 0; i < cnt; ++i) {
-                        uint32_t pth = hq[i];
-                        float rec[8] = {ho[pth].x, ho[pth].y, ho[pth].z, hd[pth].x, hd[pth].y, hd[pth].z, (float)hs[pth], (float)pth};
+                        uint32_t pth;
+                        memcpy(&pth, &qo[i].w, 4);
+                        float rec[8] = {qo[i].x, qo[i].y, qo[i].z, qd[i].x, qd[i].y, qd[i].z, (float)hs[pth], (float)pth};
                         fwrite(rec, 4, 8, f);
                     }
                     fclose(f);

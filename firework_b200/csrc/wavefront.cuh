@@ -2,10 +2,11 @@
 // Iterative form of render.rs:12-33 `color()` (depth cap 10) inside render.rs:163-196 `render_pixel`.
 //
 // Path p of a batch covers pixel  pix0 + p % npix  and sample  s0 + p / npix  (implicit mapping: no id arrays).
-// Per-path state lives in HBM as SoA float4 streams; per-bounce queues hold path ids, compacted with
-// warp ballot / popc so that one atomicAdd per warp per queue reserves the slots.  extend publishes only the
-// winning (t, object, primitive, barycentrics); the shade kernel that consumes a path rebuilds point / normal /
-// uv (finalize_hit) in registers.
+// The queues carry the path's working state with them (ray, winning hit) as SoA float4 streams in queue order,
+// compacted with warp ballot / popc, so every kernel reads its input fully coalesced and without a dependent
+// "queue entry -> path -> record" hop; only the attenuation chain and the final radiance are indexed by path.
+// extend publishes just the winning (t, object, primitive, barycentrics); the shade kernel that consumes a path
+// rebuilds point / normal / uv (finalize_hit) in registers.
 #pragma once
 #include "intersect.cuh"
 #include "shade.cuh"
@@ -30,16 +31,18 @@ constexpr int FW_BLOCK = 128;             // threads per block of every queue-dr
 // population only shrinks, so `seg_cap` = its bounce-0 share always suffices), fill counts are plain
 // shared-memory counters written back once per block, and no global atomic is issued anywhere.  (One global
 // counter per queue was the top stall of both extend and shade: ~2.5 same-sector atomics per warp iteration.)
+struct HitQueue {      // one shade queue: records of the paths whose ray hit a surface of that material
+    float4* o;         // [nseg][seg_cap] ray origin.xyz, asfloat(path)
+    float4* d;         // ray direction.xyz (never normalised: ray.rs), winning t        (miss queue: d.xyz, asfloat(path))
+    float4* w;         // asfloat(object), asfloat(primitive), asfloat(material), asfloat(rank)   (rank: two-pass extend only)
+    float4* b;         // triangle barycentrics b0, b1, b2 — allocated only for scenes with TriangleMesh objects
+};
 struct PathState {
-    float4* ray_o;     // [cap] origin.xyz
-    float4* ray_d;     // [cap] direction.xyz (never normalised: ray.rs)
-    float4* win_a;     // [cap] winning hit: t, asfloat(object), asfloat(primitive), asfloat(material)  (object -1 = miss)
-    float4* win_b;     // [cap] triangle barycentrics b0, b1, b2 (written for mesh hits only); .w = rank between passes
-    float4* atten;     // [FW_MAX_DEPTH][cap] attenuation chain (see fold_radiance)
-    float4* radiance;  // [cap] finished path radiance
-    uint32_t* q_extend[2];             // ping-pong extend queues   (all queues: [nseg][seg_cap] path ids)
-    uint32_t* q_mesh;                  // paths whose ray still has to walk a mesh (two-pass extend)
-    uint32_t* q_mat[MAT_NUM_QUEUES];   // per-material shade queues
+    float4* xo[2];     // ping-pong extend queues: ray origin.xyz, asfloat(path)
+    float4* xd[2];     //                          ray direction.xyz
+    HitQueue hq[8];    // [0..5] per-material shade queues (MatKind; MAT_MISS uses .d only), [7] mesh queue (two-pass extend)
+    float4* atten;     // [FW_MAX_DEPTH][cap] attenuation chain, by path (see fold_radiance)
+    float4* radiance;  // [cap] finished path radiance, by path
     uint32_t* counters;                // [FW_MAX_DEPTH + 2][FW_NUM_QUEUES][nseg] fill counts
     uint32_t cap;
     uint32_t nseg, seg_cap;
@@ -81,12 +84,12 @@ FW_DEV void primary_ray(const CameraRec& cam, uint32_t width, uint32_t height, u
 }
 
 // One block per segment.  Tile t (FW_TILE consecutive paths) belongs to segment t % nseg, so every segment gets an
-// even mix of the image; entry e of segment `seg` is path ((e / TILE) * nseg + seg) * TILE + e % TILE.  Besides
-// the rays, raygen writes the segment's bounce-0 extend queue, so that extend has one input form on every bounce.
+// even mix of the image; entry e of segment `seg` is path ((e / TILE) * nseg + seg) * TILE + e % TILE.  The rays
+// go straight into the segment's bounce-0 extend queue.
 __global__ void __launch_bounds__(FW_BLOCK) raygen_kernel(CameraRec cam, Batch b, uint2 seed, PathState ps) {
     const uint32_t total = b.npix * b.ns;
     const uint32_t seg = blockIdx.x;
-    uint32_t* q = ps.q_extend[0] + (size_t)seg * ps.seg_cap;
+    const size_t base = (size_t)seg * ps.seg_cap;
     uint32_t count = 0;
     for (uint32_t e = threadIdx.x; e < ps.seg_cap; e += FW_BLOCK) {
         uint32_t p = ((e / FW_TILE) * ps.nseg + seg) * FW_TILE + (e % FW_TILE);
@@ -95,10 +98,9 @@ __global__ void __launch_bounds__(FW_BLOCK) raygen_kernel(CameraRec cam, Batch b
         batch_path(b, p, pixel, sample);
         float3 o, d;
         primary_ray(cam, b.width, b.height, pixel, sample, seed, o, d);
-        ps.ray_o[p] = make_float4(o.x, o.y, o.z, 0.0f);
-        ps.ray_d[p] = make_float4(d.x, d.y, d.z, 0.0f);
+        ps.xo[0][base + e] = make_float4(o.x, o.y, o.z, __uint_as_float(p));
+        ps.xd[0][base + e] = make_float4(d.x, d.y, d.z, 0.0f);
         ps.radiance[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        q[e] = p;
         count = e + 1;
     }
     // the segment's entry count = 1 + the largest valid e over the block
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(FW_BLOCK) raygen_kernel(CameraRec cam, Batch b
     __syncthreads();
     if (count) atomicMax(&s_count, count);
     __syncthreads();
-    if (threadIdx.x == 0) counter_row(ps, 0, 6)[seg] = s_count;
+    if (threadIdx.x == 0) counter_row(ps, 0, FW_Q_EXTEND)[seg] = s_count;
 }
 
 // ---- segment plumbing ------------------------------------------------------------------------------------
@@ -125,12 +127,13 @@ FW_DEV void seg_close(const uint32_t* s_fill, const PathState& ps, uint32_t* cou
     __syncthreads();
     if (threadIdx.x < NQ) counter_rows[(size_t)threadIdx.x * ps.nseg + seg] = s_fill[threadIdx.x];
 }
-// Append `path` to queue `k` of the segment for every lane whose `mine` == k: one shared-memory atomic per warp per
-// non-empty queue reserves the slots (warp ballot / popc compaction).  All 32 lanes must call.
+// Reserve one slot in queue `mine` of the segment for every lane with 0 <= mine < NQ: one shared-memory atomic per
+// warp per non-empty queue (warp ballot / popc compaction).  Returns the slot (global index); all 32 lanes must call.
 template <int NQ>
-FW_DEV void seg_enqueue(uint32_t* const* queues, uint32_t* s_fill, uint32_t seg_base, int mine, uint32_t path) {
+FW_DEV uint32_t seg_reserve(uint32_t* s_fill, uint32_t seg_base, int mine) {
     unsigned lane = threadIdx.x & 31u;
     unsigned lt = (1u << lane) - 1u;
+    uint32_t slot = 0;
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
         unsigned mask = __ballot_sync(0xffffffffu, mine == k);
@@ -139,49 +142,80 @@ FW_DEV void seg_enqueue(uint32_t* const* queues, uint32_t* s_fill, uint32_t seg_
         uint32_t base = 0;
         if ((int)lane == leader) base = atomicAdd(&s_fill[k], (uint32_t)__popc(mask));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (mine == k) queues[k][seg_base + base + __popc(mask & lt)] = path;
+        if (mine == k) slot = seg_base + base + __popc(mask & lt);
     }
+    return slot;
 }
 
-// extend: closest hit for every queued path; writes the winning (t, object, primitive, barycentrics) and
-// sorts the path into its material's shade queue (or the miss queue).  The full hit record is rebuilt by the
+// extend: closest hit for every queued ray; the ray moves on, together with the winning (t, object, primitive,
+// barycentrics), into its material's shade queue (or the miss queue).  The full hit record is rebuilt by the
 // shade kernel that consumes it (finalize_hit), so it never travels through HBM.
 
-// Publishes a ray's result and returns the shade queue it belongs to.  The material index travels with the
-// record so that the shade kernel can fetch its material in parallel with the object records.
-FW_DEV int store_winner(const DeviceScene& S, const PathState& ps, uint32_t path, const Winner& w) {
-    if (!w.found) {
-        ps.win_a[path] = make_float4(0.0f, __int_as_float(-1), 0.0f, __int_as_float(-1));
-        return MAT_MISS;
-    }
+// The shade queue a winner belongs to, and its material (which travels with the record so that the shade kernel can
+// fetch its material in parallel with the object records).
+FW_DEV int classify_winner(const DeviceScene& S, const Winner& w, int& material) {
+    material = -1;
+    if (!w.found) return MAT_MISS;
     int4 meta = __ldg(&S.obj_meta[w.obj]);
-    int kind = meta.x & OBJ_KIND_MASK;
-    int material = meta.y;
-    if (kind == SH_RECT3D) material = winner_material(S, w.obj, w.h.prim);  // faces may carry their own material
-    ps.win_a[path] = make_float4(w.t, __int_as_float(w.obj), __int_as_float(w.h.prim), __int_as_float(material));
-    if (kind == SH_MESH) ps.win_b[path] = make_float4(w.h.b0, w.h.b1, w.h.b2, 0.0f);
+    material = meta.y;
+    if ((meta.x & OBJ_KIND_MASK) == SH_RECT3D) material = winner_material(S, w.obj, w.h.prim);  // faces may carry their own material
     return __ldg(&S.mats[material].kind);
 }
-FW_DEV Winner load_winner(const PathState& ps, uint32_t path, int& material) {
-    float4 a = ps.win_a[path];
-    Winner w;
-    w.found = true;
-    w.t = a.x; w.obj = __float_as_int(a.y); w.rank = 0;
-    w.h.t = a.x; w.h.prim = __float_as_int(a.z);
-    material = __float_as_int(a.w);
-    w.h.b0 = w.h.b1 = w.h.b2 = 0.0f;
-    return w;
+// Writes the hit record of one ray into slot `slot` of queue K (K is a compile-time constant at every call site, so
+// the queue's pointers are plain kernel parameters).
+template <int K>
+FW_DEV void put_hit(const PathState& ps, uint32_t slot, float3 o, float3 d, uint32_t path, const Winner& w, int material) {
+    if (K == MAT_MISS) {
+        ps.hq[K].d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(path));
+        return;
+    }
+    ps.hq[K].o[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(path));
+    ps.hq[K].d[slot] = make_float4(d.x, d.y, d.z, w.t);
+    ps.hq[K].w[slot] = make_float4(__int_as_float(w.obj), __int_as_float(w.h.prim), __int_as_float(material), __int_as_float(w.rank));
+    if (ps.hq[K].b) ps.hq[K].b[slot] = make_float4(w.h.b0, w.h.b1, w.h.b2, 0.0f);
 }
-// Barycentrics are only stored (and only needed) for TriangleMesh hits.
-FW_DEV void load_winner_bary(const DeviceScene& S, const PathState& ps, uint32_t path, Winner& w) {
-    if ((__ldg(&S.obj_meta[w.obj]).x & OBJ_KIND_MASK) == SH_MESH) {
-        float4 b = ps.win_b[path];
-        w.h.b0 = b.x; w.h.b1 = b.y; w.h.b2 = b.z;
+template <int NQ>
+FW_DEV void enqueue_hit(const PathState& ps, uint32_t* s_fill, uint32_t seg_base, int mine, float3 o, float3 d, uint32_t path,
+                        const Winner& w, int material) {
+    uint32_t slot = seg_reserve<NQ>(s_fill, seg_base, mine);
+    switch (mine) {   // one arm per queue keeps the queue index a compile-time constant
+        case 0: put_hit<0>(ps, slot, o, d, path, w, material); break;
+        case 1: put_hit<1>(ps, slot, o, d, path, w, material); break;
+        case 2: put_hit<2>(ps, slot, o, d, path, w, material); break;
+        case 3: put_hit<3>(ps, slot, o, d, path, w, material); break;
+        case 4: put_hit<4>(ps, slot, o, d, path, w, material); break;
+        case 5: put_hit<5>(ps, slot, o, d, path, w, material); break;
+        case FW_Q_MESH: if (NQ > FW_Q_MESH) put_hit<FW_Q_MESH>(ps, slot, o, d, path, w, material); break;
+        default: break;
     }
 }
+// A hit record read back by the kernel that consumes queue K.
+struct HitIn {
+    float3 o, d;
+    uint32_t path;
+    int material;
+    Winner w;
+};
+template <int K>
+FW_DEV HitIn get_hit(const PathState& ps, uint32_t slot) {
+    float4 A = ps.hq[K].o[slot], B = ps.hq[K].d[slot], C = ps.hq[K].w[slot];
+    HitIn h;
+    h.o = f3(A); h.d = f3(B);
+    h.path = __float_as_uint(A.w);
+    h.material = __float_as_int(C.z);
+    h.w.found = __float_as_int(C.x) >= 0;
+    h.w.t = B.w; h.w.obj = __float_as_int(C.x); h.w.rank = __float_as_int(C.w);
+    h.w.h.t = B.w; h.w.h.prim = __float_as_int(C.y);
+    h.w.h.b0 = h.w.h.b1 = h.w.h.b2 = 0.0f;
+    if (ps.hq[K].b) {   // scenes with meshes: barycentrics of the winning triangle (unused for other shapes)
+        float4 D = ps.hq[K].b[slot];
+        h.w.h.b0 = D.x; h.w.h.b1 = D.y; h.w.h.b2 = D.z;
+    }
+    return h;
+}
 
-// Common shape of the extend kernels: one block per segment, FW_BLOCK entries per iteration; `trace` maps
-// (path, o, d, key) to the shade queue of the path (after publishing the winner).
+// Common shape of the extend kernels: one block per segment, FW_BLOCK rays per iteration.  The body sets `w`
+// for valid lanes; the epilogue sorts the ray into its shade queue.
 #define FW_EXTEND_PROLOGUE(NQ_OUT)                                                                         \
     __shared__ uint32_t s_fill[FW_NUM_QUEUES];                                                               \
     const uint32_t in_count = counter_row(ps, bounce, FW_Q_EXTEND)[blockIdx.x];                              \
@@ -189,10 +223,19 @@ FW_DEV void load_winner_bary(const DeviceScene& S, const PathState& ps, uint32_t
     for (uint32_t e0 = 0; e0 < in_count; e0 += FW_BLOCK) {                                                   \
         const bool valid = e0 + threadIdx.x < in_count;                                                      \
         uint32_t path = 0;                                                                                   \
-        if (valid) path = ps.q_extend[bounce & 1][(size_t)blockIdx.x * ps.seg_cap + e0 + threadIdx.x];       \
-        int mine = -1;
-#define FW_EXTEND_EPILOGUE(NQ_OUT, QUEUES)                                                                 \
-        seg_enqueue<NQ_OUT>(QUEUES, s_fill, blockIdx.x * ps.seg_cap, mine, path);                            \
+        float3 o = f3(1e30f, 1e30f, 1e30f), d = f3(1.0f, 1.0f, 1.0f);                                        \
+        if (valid) {                                                                                         \
+            const size_t slot_in = (size_t)blockIdx.x * ps.seg_cap + e0 + threadIdx.x;                       \
+            float4 ro = ps.xo[bounce & 1][slot_in], rd = ps.xd[bounce & 1][slot_in];                         \
+            o = f3(ro); d = f3(rd); path = __float_as_uint(ro.w);                                            \
+        }                                                                                                    \
+        Winner w;                                                                                            \
+        w.found = false; w.t = 0.0f; w.obj = -1; w.rank = -1; w.h.t = 0.0f; w.h.prim = 0;                    \
+        w.h.b0 = w.h.b1 = w.h.b2 = 0.0f;                                                                     \
+        int mine = -1, material = -1;
+#define FW_EXTEND_EPILOGUE(NQ_OUT)                                                                         \
+        if (valid && mine < 0) mine = classify_winner(S, w, material);                                       \
+        enqueue_hit<NQ_OUT>(ps, s_fill, blockIdx.x * ps.seg_cap, mine, o, d, path, w, material);             \
     }                                                                                                        \
     seg_close<NQ_OUT>(s_fill, ps, counter_row(ps, bounce, 0), blockIdx.x);
 
@@ -200,50 +243,38 @@ FW_DEV void load_winner_bary(const DeviceScene& S, const PathState& ps, uint32_t
 __global__ void __launch_bounds__(FW_BLOCK) extend_bvh_debug_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
                                                                     uint32_t* steps) {
     FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
-            if (valid) {
-                float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
-                RngKey key{seed, 0u, 0u, bounce};
-                batch_path(b, path, key.pixel, key.sample);
-                Winner w;
-                Counters cnt{0, 0};
-                trace_unified<true, true>(S, o, d, key, w, &cnt);
-                steps[path] = (uint32_t)cnt.node_tests;
-                mine = store_winner(S, ps, path, w);
-            }
-    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES, ps.q_mat)
+        if (valid) {
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            Counters cnt{0, 0};
+            trace_unified<true, true>(S, o, d, key, w, &cnt);
+            steps[path] = (uint32_t)cnt.node_tests;
+        }
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
 }
 
 // Two-pass extend for BVH scenes with TriangleMesh objects (see UnifiedWalker PHASE).  Pass 1 settles every ray
-// against the non-mesh objects and the mesh root boxes; rays that must enter a mesh are compacted into q_mesh
-// and finished by pass 2, where every lane of a warp is doing real mesh traversal.
+// against the non-mesh objects and the mesh root boxes; rays that must enter a mesh are compacted into the mesh
+// queue (with the pass-1 winner and its rank) and finished by pass 2, where every lane of a warp is doing real
+// mesh traversal.
 template <bool NESTED>
 __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass1_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
                                                                                 uint32_t bounce) {
-    uint32_t* q8[FW_NUM_QUEUES];
-#pragma unroll
-    for (int k = 0; k < MAT_NUM_QUEUES; ++k) q8[k] = ps.q_mat[k];
-    q8[FW_Q_EXTEND] = nullptr;   // never selected here (slot 6 of the counter rows belongs to the shade kernels)
-    q8[FW_Q_MESH] = ps.q_mesh;
     FW_EXTEND_PROLOGUE(FW_NUM_QUEUES)
-            if (valid) {
-                float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
-                RngKey key{seed, 0u, 0u, bounce};
-                batch_path(b, path, key.pixel, key.sample);
-                UnifiedWalker<false, NESTED, true, 1> wk;
-                int stack_code[FW_STACK];
-                float stack_te[FW_STACK];
-                if (wk.init(S, o, d, stack_code, stack_te, nullptr)) {
-                    while (wk.step(S, key, nullptr)) {
-                    }
-                }
-                mine = store_winner(S, ps, path, wk.w);
-                if (wk.pending) {
-                    // pass 2 needs the rank of the pass-1 winner (a non-mesh object, so win_b is free)
-                    if (wk.w.found) ps.win_b[path] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(wk.w.rank));
-                    mine = FW_Q_MESH;
+        if (valid) {
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            UnifiedWalker<false, NESTED, true, 1> wk;
+            int stack_code[FW_STACK];
+            float stack_te[FW_STACK];
+            if (wk.init(S, o, d, stack_code, stack_te, nullptr)) {
+                while (wk.step(S, key, nullptr)) {
                 }
             }
-    FW_EXTEND_EPILOGUE(FW_NUM_QUEUES, q8)
+            w = wk.w;
+            if (wk.pending) mine = FW_Q_MESH;   // queue 6 is never selected (its counter slot belongs to the shade kernels)
+        }
+    FW_EXTEND_EPILOGUE(FW_NUM_QUEUES)
 }
 template <bool NESTED>
 __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass2_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
@@ -254,28 +285,28 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass2_k
     seg_open<MAT_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), blockIdx.x);   // continues pass 1's material queues
     for (uint32_t e0 = 0; e0 < in_count; e0 += FW_BLOCK) {
         const bool valid = e0 + threadIdx.x < in_count;
-        uint32_t path = 0;
-        int mine = -1;
+        int mine = -1, material = -1;
+        HitIn h;
+        h.path = 0; h.o = h.d = f3(0.0f, 0.0f, 0.0f);
+        h.w.found = false; h.w.t = 0.0f; h.w.obj = -1; h.w.rank = -1; h.w.h.t = 0.0f; h.w.h.prim = 0;
+        h.w.h.b0 = h.w.h.b1 = h.w.h.b2 = 0.0f;
         if (valid) {
-            path = ps.q_mesh[(size_t)blockIdx.x * ps.seg_cap + e0 + threadIdx.x];
-            float3 o = f3(ps.ray_o[path]), d = f3(ps.ray_d[path]);
+            h = get_hit<FW_Q_MESH>(ps, blockIdx.x * ps.seg_cap + e0 + threadIdx.x);
             RngKey key{seed, 0u, 0u, bounce};
-            batch_path(b, path, key.pixel, key.sample);
+            batch_path(b, h.path, key.pixel, key.sample);
             UnifiedWalker<false, NESTED, true, 2> wk;
-            float4 a = ps.win_a[path];
-            wk.w.found = __float_as_int(a.y) >= 0;
-            wk.w.t = a.x; wk.w.obj = __float_as_int(a.y); wk.w.rank = -1;
-            wk.w.h.t = a.x; wk.w.h.prim = __float_as_int(a.z); wk.w.h.b0 = wk.w.h.b1 = wk.w.h.b2 = 0.0f;
-            if (wk.w.found) wk.w.rank = __float_as_int(ps.win_b[path].w);
+            wk.w = h.w;   // the pass-1 winner (a non-mesh object) and its rank
+            wk.w.h.b0 = wk.w.h.b1 = wk.w.h.b2 = 0.0f;
             int stack_code[FW_STACK];
             float stack_te[FW_STACK];
-            if (wk.init(S, o, d, stack_code, stack_te, nullptr)) {
+            if (wk.init(S, h.o, h.d, stack_code, stack_te, nullptr)) {
                 while (wk.step(S, key, nullptr)) {
                 }
             }
-            mine = store_winner(S, ps, path, wk.w);
+            h.w = wk.w;
+            mine = classify_winner(S, h.w, material);
         }
-        seg_enqueue<MAT_NUM_QUEUES>(ps.q_mat, s_fill, blockIdx.x * ps.seg_cap, mine, path);
+        enqueue_hit<MAT_NUM_QUEUES>(ps, s_fill, blockIdx.x * ps.seg_cap, mine, h.o, h.d, h.path, h.w, material);
     }
     seg_close<MAT_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), blockIdx.x);
 }
@@ -284,16 +315,12 @@ template <bool NESTED, bool MESHES>
 __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
                                                                                      uint32_t bounce) {
     FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
-            if (valid) {
-                float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
-                float3 o = f3(ro), d = f3(rd);
-                RngKey key{seed, 0u, 0u, bounce};
-                batch_path(b, path, key.pixel, key.sample);
-                Winner w;
-                trace_unified<false, NESTED, MESHES>(S, o, d, key, w, nullptr);
-                mine = store_winner(S, ps, path, w);
-            }
-    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES, ps.q_mat)
+        if (valid) {
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            trace_unified<false, NESTED, MESHES>(S, o, d, key, w, nullptr);
+        }
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
 }
 
 // Linear-scan scenes (Renderer.use_bvh == false, scene.rs:137-149): every ray tests every object in scene
@@ -303,16 +330,12 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_bvh_sim
 template <bool NESTED>
 __global__ void __launch_bounds__(FW_BLOCK) extend_linear_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce) {
     FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
-            if (valid) {
-                float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
-                float3 o = f3(ro), d = f3(rd);
-                RngKey key{seed, 0u, 0u, bounce};
-                batch_path(b, path, key.pixel, key.sample);
-                Winner w;
-                trace_linear_scan<false, NESTED>(S, o, d, key, w, nullptr);
-                mine = store_winner(S, ps, path, w);
-            }
-    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES, ps.q_mat)
+        if (valid) {
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            trace_linear_scan<false, NESTED>(S, o, d, key, w, nullptr);
+        }
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
 }
 
 // The same query driven by the scene's LinProgram in kernel-parameter space (intersect.cuh trace_linear_prog):
@@ -322,17 +345,10 @@ template <bool GENERIC, bool NESTED, bool PRETEST>
 __global__ void __launch_bounds__(FW_BLOCK) extend_linear_prog_kernel(const __grid_constant__ LinProgram P, DeviceScene S, PathState ps,
                                                                       Batch b, uint2 seed, uint32_t bounce) {
     FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
-            float3 o = f3(1e30f, 1e30f, 1e30f), d = f3(1.0f, 1.0f, 1.0f);
-            if (valid) {
-                float4 ro = ps.ray_o[path], rd = ps.ray_d[path];
-                o = f3(ro); d = f3(rd);
-            }
-            RngKey key{seed, 0u, 0u, bounce};
-            if (GENERIC) batch_path(b, path, key.pixel, key.sample);
-            Winner w;
-            trace_linear_prog<false, GENERIC, NESTED, PRETEST>(P, S, o, d, key, w, nullptr);
-            if (valid) mine = store_winner(S, ps, path, w);
-    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES, ps.q_mat)
+        RngKey key{seed, 0u, 0u, bounce};
+        if (GENERIC) batch_path(b, path, key.pixel, key.sample);
+        trace_linear_prog<false, GENERIC, NESTED, PRETEST>(P, S, o, d, key, w, nullptr);
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
 }
 
 // render.rs:23 evaluated without recursion: colour = a0 * (a1 * (... (a_{k-1} * terminal))) with the same
@@ -353,95 +369,88 @@ FW_DEV float3 fold_radiance(const PathState& ps, uint32_t path, uint32_t bounce,
 
 // render.rs:31 — environment lookup for rays that left the scene
 __global__ void __launch_bounds__(FW_BLOCK) miss_kernel(DeviceScene S, PathState ps, uint32_t bounce) {
-    {
-        const uint32_t total = counter_row(ps, bounce, MAT_MISS)[blockIdx.x];
-        const uint32_t* qs = ps.q_mat[MAT_MISS] + (size_t)blockIdx.x * ps.seg_cap;
-        for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
-            uint32_t path = qs[i];
-            float3 env = environment_sample(S.env, f3(ps.ray_d[path]));
-            float3 c = fold_radiance(ps, path, bounce, env);
-            ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
-        }
+    const uint32_t total = counter_row(ps, bounce, MAT_MISS)[blockIdx.x];
+    const float4* qd = ps.hq[MAT_MISS].d + (size_t)blockIdx.x * ps.seg_cap;
+    for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
+        float4 rec = qd[i];
+        uint32_t path = __float_as_uint(rec.w);
+        float3 env = environment_sample(S.env, f3(rec));
+        float3 c = fold_radiance(ps, path, bounce, env);
+        ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
     }
 }
 
 // render.rs:20,25-28 with material.rs:174-180 — emissive surfaces end the path with their texture value
 __global__ void __launch_bounds__(FW_BLOCK) shade_emissive_kernel(DeviceScene S, PathState ps, uint32_t bounce) {
-    {
-        const uint32_t total = counter_row(ps, bounce, MAT_EMISSIVE)[blockIdx.x];
-        const uint32_t* qs = ps.q_mat[MAT_EMISSIVE] + (size_t)blockIdx.x * ps.seg_cap;
-        for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
-            uint32_t path = qs[i];
-            int material;
-            Winner w = load_winner(ps, path, material);
-            load_winner_bary(S, ps, path, w);
-            HitRecord rec;
-            finalize_hit(S, w, f3(ps.ray_o[path]), f3(ps.ray_d[path]), rec, true);
-            int tex = __ldg(&S.mats[material].tex);
-            float3 emit = texture_sample(S, tex, rec.uv, rec.point);
-            float3 c = fold_radiance(ps, path, bounce, emit);
-            ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
-        }
+    const uint32_t total = counter_row(ps, bounce, MAT_EMISSIVE)[blockIdx.x];
+    const uint32_t base = blockIdx.x * ps.seg_cap;
+    for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
+        HitIn h = get_hit<MAT_EMISSIVE>(ps, base + i);
+        HitRecord rec;
+        finalize_hit(S, h.w, h.o, h.d, rec, true);
+        int tex = __ldg(&S.mats[h.material].tex);
+        float3 emit = texture_sample(S, tex, rec.uv, rec.point);
+        float3 c = fold_radiance(ps, h.path, bounce, emit);
+        ps.radiance[h.path] = make_float4(c.x, c.y, c.z, 0.0f);
     }
 }
 
-// Scattering materials: write the next ray + this vertex's attenuation, re-queue the path for extend.
+// Scattering materials: the next ray goes into the next extend queue, this vertex's attenuation into the chain.
 // Not launched for bounce == FW_MAX_DEPTH (render.rs:21: no scatter at depth 10; emit is zero).
 // The material kernels of one bounce run back to back and append to the same regions of the next extend queue.
 template <int MAT>
 __global__ void __launch_bounds__(FW_BLOCK, FW_SHADE_MIN_BLOCKS) shade_scatter_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce) {
     __shared__ uint32_t s_fill[1];
+    const uint32_t seg = blockIdx.x;
+    const uint32_t total = counter_row(ps, bounce, MAT)[seg];
+    if (total == 0) return;  // block-uniform
     uint32_t* row_out = counter_row(ps, bounce + 1, FW_Q_EXTEND);
-    const uint32_t* q = ps.q_mat[MAT];
-    uint32_t* q_out = ps.q_extend[(bounce + 1) & 1];
-    {
-        const uint32_t seg = blockIdx.x;
-        const uint32_t total = counter_row(ps, bounce, MAT)[seg];
-        if (total == 0) return;  // block-uniform
-        const uint32_t base = seg * ps.seg_cap;
-        seg_open<1>(s_fill, ps, row_out, seg);
-        for (uint32_t e0 = 0; e0 < total; e0 += FW_BLOCK) {
-            uint32_t i = e0 + threadIdx.x;
-            int mine = -1;
-            uint32_t path = 0;
-            if (i < total) {
-                path = q[base + i];
-                float3 in_o = f3(ps.ray_o[path]), in_d = f3(ps.ray_d[path]);
-                int material;
-                Winner w = load_winner(ps, path, material);
-                const float4* mq = reinterpret_cast<const float4*>(&S.mats[material]);
-                float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);  // (kind, tex, param, needs_uv), (albedo, -)
-                load_winner_bary(S, ps, path, w);
-                HitRecord rec;
-                finalize_hit(S, w, in_o, in_d, rec, __float_as_int(m0.w) != 0);
-                float3 point = rec.point, normal = rec.normal;
-                uint32_t pixel, sample;
-                batch_path(b, path, pixel, sample);
-                RngKey key{seed, pixel, sample, bounce};
-                PhiloxStream rng(key, STREAM_SCATTER);
-                ScatterOut out;
-                if (MAT == MAT_LAMBERTIAN) {
-                    scatter_lambertian(S, __float_as_int(m0.y), point, normal, rec.uv, rng, out);
-                } else if (MAT == MAT_METAL) {
-                    scatter_metal(f3(m1), m0.z, in_d, point, normal, rng, out);
-                } else if (MAT == MAT_DIELECTRIC) {
-                    scatter_dielectric(m0.z, in_d, point, normal, rng, out);
-                } else {
-                    scatter_isotropic(S, __float_as_int(m0.y), point, rec.uv, rng, out);
-                }
-                if (out.scattered) {
-                    ps.ray_o[path] = make_float4(out.origin.x, out.origin.y, out.origin.z, 0.0f);
-                    ps.ray_d[path] = make_float4(out.dir.x, out.dir.y, out.dir.z, 0.0f);
-                    ps.atten[(size_t)bounce * ps.cap + path] =
-                        make_float4(out.attenuation.x, out.attenuation.y, out.attenuation.z, 0.0f);
-                    mine = 0;
-                }
-                // absorbed (metal below the surface): radiance stays 0 (render.rs:25)
+    const uint32_t base = seg * ps.seg_cap;
+    float4* __restrict__ xo = ps.xo[(bounce + 1) & 1];
+    float4* __restrict__ xd = ps.xd[(bounce + 1) & 1];
+    seg_open<1>(s_fill, ps, row_out, seg);
+    for (uint32_t e0 = 0; e0 < total; e0 += FW_BLOCK) {
+        uint32_t i = e0 + threadIdx.x;
+        int mine = -1;
+        uint32_t path = 0;
+        ScatterOut out;
+        out.scattered = false;
+        out.origin = out.dir = out.attenuation = f3(0.0f, 0.0f, 0.0f);
+        if (i < total) {
+            HitIn h = get_hit<MAT>(ps, base + i);
+            path = h.path;
+            const float4* mq = reinterpret_cast<const float4*>(&S.mats[h.material]);
+            float4 m0 = __ldg(mq), m1 = __ldg(mq + 1);  // (kind, tex, param, needs_uv), (albedo, -)
+            HitRecord rec;
+            finalize_hit(S, h.w, h.o, h.d, rec, __float_as_int(m0.w) != 0);
+            float3 point = rec.point, normal = rec.normal;
+            uint32_t pixel, sample;
+            batch_path(b, path, pixel, sample);
+            RngKey key{seed, pixel, sample, bounce};
+            PhiloxStream rng(key, STREAM_SCATTER);
+            if (MAT == MAT_LAMBERTIAN) {
+                scatter_lambertian(S, __float_as_int(m0.y), point, normal, rec.uv, rng, out);
+            } else if (MAT == MAT_METAL) {
+                scatter_metal(f3(m1), m0.z, h.d, point, normal, rng, out);
+            } else if (MAT == MAT_DIELECTRIC) {
+                scatter_dielectric(m0.z, h.d, point, normal, rng, out);
+            } else {
+                scatter_isotropic(S, __float_as_int(m0.y), point, rec.uv, rng, out);
             }
-            seg_enqueue<1>(&q_out, s_fill, base, mine, path);
+            if (out.scattered) {
+                ps.atten[(size_t)bounce * ps.cap + path] =
+                    make_float4(out.attenuation.x, out.attenuation.y, out.attenuation.z, 0.0f);
+                mine = 0;
+            }
+            // absorbed (metal below the surface): radiance stays 0 (render.rs:25)
         }
-        seg_close<1>(s_fill, ps, row_out, seg);
+        uint32_t slot = seg_reserve<1>(s_fill, base, mine);
+        if (mine == 0) {
+            xo[slot] = make_float4(out.origin.x, out.origin.y, out.origin.z, __uint_as_float(path));
+            xd[slot] = make_float4(out.dir.x, out.dir.y, out.dir.z, 0.0f);
+        }
     }
+    seg_close<1>(s_fill, ps, row_out, seg);
 }
 
 // Ray statistics without a host round trip per batch: rays traced = every entry of every bounce's extend queue.
