@@ -42,7 +42,7 @@ EXPORTS = [
     "fw_scene_num_nodes", "fw_scene_device_bytes", "fw_scene_top_leaf_order", "fw_scene_object_aabb", "fw_scene_mesh_leaf_order", "fw_scene_linear_program", "fw_render",
     "fw_render_accumulate_device", "fw_resolve_device", "fw_primary_rays", "fw_first_hit", "fw_scatter_step",
     "fw_env_sample", "fw_texture_sample", "fw_material_texture", "fw_camera", "fw_last_error", "fw_version",
-    "fw_device_count", "fw_measure_peaks", "fw_set_profiling", "fw_set_batch_paths", "fw_release_cached_memory",
+    "fw_device_count", "fw_measure_peaks", "fw_selftest_shared_division", "fw_set_profiling", "fw_set_batch_paths", "fw_release_cached_memory",
 ]
 
 _lib = None

@@ -628,14 +628,15 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
             const LinProgram& P = sc->lin_prog;
             if (sc->flat.lin_generic) {
                 if (sc->flat.has_mesh)
-                    extend_linear_prog_kernel<true, true, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+                    extend_linear_prog_kernel<true, true, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
                 else
-                    extend_linear_prog_kernel<true, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
-            } else if (bounce == 0) {
+                    extend_linear_prog_kernel<true, false, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+            } else if (sc->flat.lin_rect_tests >= 8) {   // rectangle-heavy: shared-reciprocal division (SHDIV)
                 // coherent primary rays: whole warps skip Rect3d boxes they do not enter (PRETEST)
-                extend_linear_prog_kernel<false, false, true><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+                if (bounce == 0) extend_linear_prog_kernel<false, false, true, true><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+                else extend_linear_prog_kernel<false, false, false, true><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
             } else {
-                extend_linear_prog_kernel<false, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+                extend_linear_prog_kernel<false, false, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
             }
         } else if (sc->flat.has_mesh) {
             extend_linear_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
@@ -909,6 +910,21 @@ int fw_texture_sample(fw_scene* sc, int texture, uint32_t n, const float* uv, co
     FW_CUDA(cudaGetLastError());
     FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     return o.get(out, (size_t)n * 12);
+}
+
+int fw_selftest_shared_division(int device, uint64_t n_pairs, uint64_t seed, uint64_t violations[2]) {
+    if (!violations) return set_error(FW_ERR_ARG, "null argument");
+    int ndev = 0;
+    FW_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return set_error(FW_ERR_CUDA, "no such CUDA device " + std::to_string(device));
+    FW_CUDA(cudaSetDevice(device));
+    DevBuf v;
+    TRY(v.alloc(16));
+    FW_CUDA(cudaMemset(v.p, 0, 16));
+    shared_division_probe<<<148 * 8, 256>>>(n_pairs, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), v.as<unsigned long long>());
+    FW_CUDA(cudaGetLastError());
+    FW_CUDA(cudaDeviceSynchronize());
+    return v.get(violations, 16);
 }
 
 // ---- roofline denominators ------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ enum LinItem : int {   // one bit per type: the dispatch is a chain of bit tests
     LIN_SPHERE = 16,   // 1 word : (radius, type, obj, -)                                               (sphere.rs:32-50)
     LIN_GENERIC = 32,  // 1 word : (-, type, obj, -): any other object, through object_test on the world ray
 };
+constexpr int LIN_SPACE_HAS_RECTS = 0x100;  // on XFORM items: rectangle items follow in this space (set up the shared division)
 constexpr int FW_LIN_MAX_WORDS = 160;   // 2.5 KiB of the 4 KiB kernel-parameter space
 struct LinProgram {
     float4 w[FW_LIN_MAX_WORDS];

@@ -764,6 +764,8 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         std::vector<float4>& W = out.lin_words;
         bool world = true;            // the kernel starts in world space (position +0, unrotated)
         int space_obj = -1;           // object whose transform defines the current space (when !world)
+        bool space_has_rects = false; // the current space's XFORM item carries LIN_SPACE_HAS_RECTS
+        size_t xform_word = 0;        // index of the current space's XFORM item
         auto bits_eq = [](float a, float b) { return memcmp(&a, &b, 4) == 0; };
         auto is_pzero = [](float a) { uint32_t u; memcpy(&u, &a, 4); return u == 0u; };  // +0.0 only: x - (+0) == x exactly
         for (size_t i = 0; i < nobj; ++i) {
@@ -784,15 +786,27 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
                 const ObjectDesc& q = desc.objects[space_obj];
                 same = bits_eq(q.position.x, o.position.x) && bits_eq(q.position.y, o.position.y) && bits_eq(q.position.z, o.position.z);
             }
-            if (!same) {
+            const bool rects = s.kind != SH_SPHERE;
+            // the kernel starts in world space WITHOUT the shared-division state: a space whose first rectangle
+            // arrives later (or the initial world space) gets an XFORM item that sets it up
+            if (!same || (rects && !space_has_rects)) {
+                xform_word = W.size();
                 W.push_back(float4{o.position.x, as_float(rotated ? LIN_XFORM_R : LIN_XFORM_T), o.position.y, o.position.z});
                 if (rotated) for (int c = 0; c < 3; ++c) W.push_back(out.obj_irot[3 * i + c]);
                 world = want_world;
                 space_obj = (int)i;
+                space_has_rects = false;
+            }
+            if (rects && !space_has_rects) {
+                int tpw;
+                memcpy(&tpw, &W[xform_word].y, 4);
+                W[xform_word].y = as_float(tpw | LIN_SPACE_HAS_RECTS);
+                space_has_rects = true;
             }
             if (s.kind == SH_SPHERE) {
                 W.push_back(float4{s.f[0], as_float(LIN_SPHERE), as_float((int)i), 0});
             } else if (s.kind == SH_RECT) {
+                out.lin_rect_tests += 1;
                 W.push_back(float4{s.f[4], as_float(LIN_RECT | ((s.i0 & 3) << 8)), as_float((int)i), as_float(0)});
                 W.push_back(float4{s.f[0], s.f[1], s.f[2], s.f[3]});
             } else {
@@ -811,6 +825,7 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
                     for (int k = 0; canon && k < 6; ++k)
                         for (int c = 0; canon && c < 5; ++c) canon = bits_eq(f[k].f[c], exp[k][c]);
                 }
+                out.lin_rect_tests += s.i1;
                 if (canon) {
                     W.push_back(float4{lo[0], as_float(LIN_BOX6), as_float((int)i), lo[1]});
                     W.push_back(float4{lo[2], hi[0], hi[1], hi[2]});

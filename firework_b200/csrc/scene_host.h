@@ -76,6 +76,7 @@ struct HostFlat {
     std::vector<int> top_items;
     std::vector<float4> lin_words;  // linear-scan program (fw_types.h LinItem), END-terminated
     bool lin_generic = false;       // the program contains LIN_GENERIC items
+    int lin_rect_tests = 0;         // AARect::hit calls per ray in the program (RECT items + 6 per BOX6)
     std::vector<float4> obj_posr, leaf_posr;
     std::vector<int4> obj_meta, leaf_meta;
     std::vector<float4> obj_rot, obj_irot;

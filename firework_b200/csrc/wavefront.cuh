@@ -31,6 +31,14 @@ constexpr int FW_BLOCK = 128;             // threads per block of every queue-dr
 // population only shrinks, so `seg_cap` = its bounce-0 share always suffices), fill counts are plain
 // shared-memory counters written back once per block, and no global atomic is issued anywhere.  (One global
 // counter per queue was the top stall of both extend and shade: ~2.5 same-sector atomics per warp iteration.)
+// Path-state streams are touched once per kernel: load / store them with the streaming (evict-first) policy so
+// that they do not push the scene tables (nodes, objects, shapes, materials) out of L1.
+#ifndef FW_STREAM_HINTS
+#define FW_STREAM_HINTS 1
+#endif
+FW_DEV float4 ld_stream(const float4* p) { return FW_STREAM_HINTS ? __ldcs(p) : *p; }
+FW_DEV void st_stream(float4* p, float4 v) { if (FW_STREAM_HINTS) __stcs(p, v); else *p = v; }
+
 struct HitQueue {      // one shade queue: records of the paths whose ray hit a surface of that material
     float4* o;         // [nseg][seg_cap] ray origin.xyz, asfloat(path)
     float4* d;         // ray direction.xyz (never normalised: ray.rs), winning t        (miss queue: d.xyz, asfloat(path))
@@ -98,9 +106,9 @@ __global__ void __launch_bounds__(FW_BLOCK) raygen_kernel(CameraRec cam, Batch b
         batch_path(b, p, pixel, sample);
         float3 o, d;
         primary_ray(cam, b.width, b.height, pixel, sample, seed, o, d);
-        ps.xo[0][base + e] = make_float4(o.x, o.y, o.z, __uint_as_float(p));
-        ps.xd[0][base + e] = make_float4(d.x, d.y, d.z, 0.0f);
-        ps.radiance[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        st_stream(&ps.xo[0][base + e], make_float4(o.x, o.y, o.z, __uint_as_float(p)));
+        st_stream(&ps.xd[0][base + e], make_float4(d.x, d.y, d.z, 0.0f));
+        st_stream(&ps.radiance[p], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
         count = e + 1;
     }
     // the segment's entry count = 1 + the largest valid e over the block
@@ -166,13 +174,13 @@ FW_DEV int classify_winner(const DeviceScene& S, const Winner& w, int& material)
 template <int K>
 FW_DEV void put_hit(const PathState& ps, uint32_t slot, float3 o, float3 d, uint32_t path, const Winner& w, int material) {
     if (K == MAT_MISS) {
-        ps.hq[K].d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(path));
+        st_stream(&ps.hq[K].d[slot], make_float4(d.x, d.y, d.z, __uint_as_float(path)));
         return;
     }
-    ps.hq[K].o[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(path));
-    ps.hq[K].d[slot] = make_float4(d.x, d.y, d.z, w.t);
-    ps.hq[K].w[slot] = make_float4(__int_as_float(w.obj), __int_as_float(w.h.prim), __int_as_float(material), __int_as_float(w.rank));
-    if (ps.hq[K].b) ps.hq[K].b[slot] = make_float4(w.h.b0, w.h.b1, w.h.b2, 0.0f);
+    st_stream(&ps.hq[K].o[slot], make_float4(o.x, o.y, o.z, __uint_as_float(path)));
+    st_stream(&ps.hq[K].d[slot], make_float4(d.x, d.y, d.z, w.t));
+    st_stream(&ps.hq[K].w[slot], make_float4(__int_as_float(w.obj), __int_as_float(w.h.prim), __int_as_float(material), __int_as_float(w.rank)));
+    if (ps.hq[K].b) st_stream(&ps.hq[K].b[slot], make_float4(w.h.b0, w.h.b1, w.h.b2, 0.0f));
 }
 template <int NQ>
 FW_DEV void enqueue_hit(const PathState& ps, uint32_t* s_fill, uint32_t seg_base, int mine, float3 o, float3 d, uint32_t path,
@@ -198,7 +206,7 @@ struct HitIn {
 };
 template <int K>
 FW_DEV HitIn get_hit(const PathState& ps, uint32_t slot) {
-    float4 A = ps.hq[K].o[slot], B = ps.hq[K].d[slot], C = ps.hq[K].w[slot];
+    float4 A = ld_stream(&ps.hq[K].o[slot]), B = ld_stream(&ps.hq[K].d[slot]), C = ld_stream(&ps.hq[K].w[slot]);
     HitIn h;
     h.o = f3(A); h.d = f3(B);
     h.path = __float_as_uint(A.w);
@@ -208,7 +216,7 @@ FW_DEV HitIn get_hit(const PathState& ps, uint32_t slot) {
     h.w.h.t = B.w; h.w.h.prim = __float_as_int(C.y);
     h.w.h.b0 = h.w.h.b1 = h.w.h.b2 = 0.0f;
     if (ps.hq[K].b) {   // scenes with meshes: barycentrics of the winning triangle (unused for other shapes)
-        float4 D = ps.hq[K].b[slot];
+        float4 D = ld_stream(&ps.hq[K].b[slot]);
         h.w.h.b0 = D.x; h.w.h.b1 = D.y; h.w.h.b2 = D.z;
     }
     return h;
@@ -226,7 +234,7 @@ FW_DEV HitIn get_hit(const PathState& ps, uint32_t slot) {
         float3 o = f3(1e30f, 1e30f, 1e30f), d = f3(1.0f, 1.0f, 1.0f);                                        \
         if (valid) {                                                                                         \
             const size_t slot_in = (size_t)blockIdx.x * ps.seg_cap + e0 + threadIdx.x;                       \
-            float4 ro = ps.xo[bounce & 1][slot_in], rd = ps.xd[bounce & 1][slot_in];                         \
+            float4 ro = ld_stream(&ps.xo[bounce & 1][slot_in]), rd = ld_stream(&ps.xd[bounce & 1][slot_in]);     \
             o = f3(ro); d = f3(rd); path = __float_as_uint(ro.w);                                            \
         }                                                                                                    \
         Winner w;                                                                                            \
@@ -341,13 +349,13 @@ __global__ void __launch_bounds__(FW_BLOCK) extend_linear_kernel(DeviceScene S, 
 // The same query driven by the scene's LinProgram in kernel-parameter space (intersect.cuh trace_linear_prog):
 // no per-lane loads of scene records, uniform item dispatch.  Every lane of a warp runs the program (lanes past
 // the end of the segment trace a dummy ray and drop the result) so that the PRETEST vote sees the whole warp.
-template <bool GENERIC, bool NESTED, bool PRETEST>
+template <bool GENERIC, bool NESTED, bool PRETEST, bool SHDIV>
 __global__ void __launch_bounds__(FW_BLOCK) extend_linear_prog_kernel(const __grid_constant__ LinProgram P, DeviceScene S, PathState ps,
                                                                       Batch b, uint2 seed, uint32_t bounce) {
     FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
         RngKey key{seed, 0u, 0u, bounce};
         if (GENERIC) batch_path(b, path, key.pixel, key.sample);
-        trace_linear_prog<false, GENERIC, NESTED, PRETEST>(P, S, o, d, key, w, nullptr);
+        trace_linear_prog<false, GENERIC, NESTED, PRETEST, SHDIV>(P, S, o, d, key, w, nullptr);
     FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
 }
 
@@ -359,7 +367,7 @@ FW_DEV float3 fold_radiance(const PathState& ps, uint32_t path, uint32_t bounce,
     float4 a[FW_MAX_DEPTH];
 #pragma unroll
     for (int k = 0; k < FW_MAX_DEPTH; ++k)
-        if (k < (int)bounce) a[k] = ps.atten[(size_t)k * ps.cap + path];
+        if (k < (int)bounce) a[k] = ld_stream(&ps.atten[(size_t)k * ps.cap + path]);
     float3 x = terminal;
 #pragma unroll
     for (int k = FW_MAX_DEPTH - 1; k >= 0; --k)
@@ -372,11 +380,11 @@ __global__ void __launch_bounds__(FW_BLOCK) miss_kernel(DeviceScene S, PathState
     const uint32_t total = counter_row(ps, bounce, MAT_MISS)[blockIdx.x];
     const float4* qd = ps.hq[MAT_MISS].d + (size_t)blockIdx.x * ps.seg_cap;
     for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
-        float4 rec = qd[i];
+        float4 rec = ld_stream(&qd[i]);
         uint32_t path = __float_as_uint(rec.w);
         float3 env = environment_sample(S.env, f3(rec));
         float3 c = fold_radiance(ps, path, bounce, env);
-        ps.radiance[path] = make_float4(c.x, c.y, c.z, 0.0f);
+        st_stream(&ps.radiance[path], make_float4(c.x, c.y, c.z, 0.0f));
     }
 }
 
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(FW_BLOCK) shade_emissive_kernel(DeviceScene S,
         int tex = __ldg(&S.mats[h.material].tex);
         float3 emit = texture_sample(S, tex, rec.uv, rec.point);
         float3 c = fold_radiance(ps, h.path, bounce, emit);
-        ps.radiance[h.path] = make_float4(c.x, c.y, c.z, 0.0f);
+        st_stream(&ps.radiance[h.path], make_float4(c.x, c.y, c.z, 0.0f));
     }
 }
 
@@ -438,16 +446,16 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_SHADE_MIN_BLOCKS) shade_scatter_k
                 scatter_isotropic(S, __float_as_int(m0.y), point, rec.uv, rng, out);
             }
             if (out.scattered) {
-                ps.atten[(size_t)bounce * ps.cap + path] =
-                    make_float4(out.attenuation.x, out.attenuation.y, out.attenuation.z, 0.0f);
+                st_stream(&ps.atten[(size_t)bounce * ps.cap + path],
+                          make_float4(out.attenuation.x, out.attenuation.y, out.attenuation.z, 0.0f));
                 mine = 0;
             }
             // absorbed (metal below the surface): radiance stays 0 (render.rs:25)
         }
         uint32_t slot = seg_reserve<1>(s_fill, base, mine);
         if (mine == 0) {
-            xo[slot] = make_float4(out.origin.x, out.origin.y, out.origin.z, __uint_as_float(path));
-            xd[slot] = make_float4(out.dir.x, out.dir.y, out.dir.z, 0.0f);
+            st_stream(&xo[slot], make_float4(out.origin.x, out.origin.y, out.origin.z, __uint_as_float(path)));
+            st_stream(&xd[slot], make_float4(out.dir.x, out.dir.y, out.dir.z, 0.0f));
         }
     }
     seg_close<1>(s_fill, ps, row_out, seg);
@@ -477,7 +485,7 @@ __global__ void __launch_bounds__(256) accumulate_kernel(float* __restrict__ sum
         size_t pix = (size_t)b.pix0 + pl;
         float r = sum[3 * pix], g = sum[3 * pix + 1], bl = sum[3 * pix + 2];
         for (uint32_t s = 0; s < b.ns; ++s) {
-            float4 c = ps.radiance[(size_t)s * b.npix + pl];
+            float4 c = ld_stream(&ps.radiance[(size_t)s * b.npix + pl]);
             r += c.x; g += c.y; bl += c.z;
         }
         sum[3 * pix] = r; sum[3 * pix + 1] = g; sum[3 * pix + 2] = bl;
@@ -557,7 +565,7 @@ __global__ void first_hit_prog_probe(const __grid_constant__ LinProgram P, Devic
         float3 d = f3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
         RngKey key{seed, pixel ? pixel[i] : i, sample ? sample[i] : 0u, bounce ? bounce[i] : 0u};
         Winner w;
-        trace_linear_prog<true, GENERIC, true, false>(P, S, o, d, key, w, &cnt);
+        trace_linear_prog<true, GENERIC, true, false, !GENERIC>(P, S, o, d, key, w, &cnt);
         if (w.found) {
             HitRecord rec;
             finalize_hit(S, w, o, d, rec);
@@ -615,6 +623,38 @@ __global__ void scatter_step_probe(DeviceScene S, uint32_t n, ScatterProbeIO io)
         io.out_d[3 * i] = out.dir.x; io.out_d[3 * i + 1] = out.dir.y; io.out_d[3 * i + 2] = out.dir.z;
         io.consumed[i] = rng.overrun ? -1 : rng.i;
     }
+}
+
+// Self-test of intersect.cuh div_by / shared_div against the hardware's IEEE `/`: pseudo-random and adversarial
+// operands around and inside the fast domain.  violations[0] counts results that differ in any bit where the helper
+// promises the exact quotient (|n| >= 2^-60 or outside the fast domain), violations[1] counts tiny-numerator cases
+// where either value reaches the only threshold it is ever compared with (t_min = 0.001).
+__global__ void shared_division_probe(uint64_t n_pairs, uint2 seed, unsigned long long* violations) {
+    unsigned long long bad = 0, bad_tiny = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0x5d1fu, 7u), seed);
+        // mantissas: random, or one of the adversarial patterns
+        const uint32_t pat[8] = {0x000000u, 0x7fffffu, 0x000001u, 0x7ffffeu, 0x400000u, 0x3fffffu, 0x555555u, 0x2aaaaau};
+        uint32_t mn = (r.z & 8u) ? pat[r.z & 7u] : (r.x & 0x7fffffu);
+        uint32_t md = (r.z & 128u) ? pat[(r.z >> 4) & 7u] : (r.y & 0x7fffffu);
+        int en = -70 + (int)((r.w & 0xffffu) % 133u);        // 2^-70 .. 2^62
+        int ed = -42 + (int)((r.w >> 16) % 85u);              // 2^-42 .. 2^42
+        uint32_t sn = (r.x >> 31) << 31, sd = (r.y >> 31) << 31;
+        float n = __uint_as_float(sn | ((uint32_t)(en + 127) << 23) | mn);
+        float d = __uint_as_float(sd | ((uint32_t)(ed + 127) << 23) | md);
+        if ((r.z & 0xff00u) == 0x1100u) n = __uint_as_float(sn);   // exact zero numerators
+        float want = n / d;
+        float got = div_by<true>(n, d, shared_div(d));
+        bool in_domain = fabsf(d) >= 9.094947017729282e-13f && fabsf(d) <= 1.099511627776e12f && fabsf(n) <= 1.152921504606846976e18f;
+        bool tiny = in_domain && fabsf(n) < 8.673617379884035e-19f;   // 2^-60
+        if (tiny) {
+            if (!(fabsf(want) < 0.001f) || !(fabsf(got) < 0.001f)) ++bad_tiny;
+        } else if (__float_as_uint(want) != __float_as_uint(got)) {
+            ++bad;
+        }
+    }
+    if (bad) atomicAdd(&violations[0], bad);
+    if (bad_tiny) atomicAdd(&violations[1], bad_tiny);
 }
 
 __global__ void env_sample_probe(DeviceScene S, uint32_t n, const float* dirs, float* out) {

@@ -193,6 +193,13 @@ def measure_peaks(device=0):
     return {"fp32_tflops": f.value, "l2_gbs": l.value, "sm_count": sm.value, "sm_clock_khz": khz.value}
 
 
+def selftest_shared_division(n_pairs: int, seed: int = 1, device: int = 0):
+    """fw_selftest_shared_division: (bit mismatches, tiny-numerator threshold violations); both must be 0."""
+    v = np.zeros(2, np.uint64)
+    N.check(N.lib().fw_selftest_shared_division(device, C.c_uint64(n_pairs), C.c_uint64(seed), N.ptr(v)))
+    return int(v[0]), int(v[1])
+
+
 def render_scene(scene, renderer, device: int = 0):
     """`Renderer::render(scene)` on one GPU: YAML -> native scene -> fw_render. Returns (rgb, sum, stats)."""
     ns = NativeScene.from_scene(scene, device)

@@ -135,6 +135,12 @@ int fw_camera(const fw_params* params, float out24[24]);        /* camera.rs:74-
 const char* fw_last_error(void);
 const char* fw_version(void);
 int fw_device_count(void);
+/* Self-test of the shared-reciprocal division used by the linear-scan kernels (t = (k - o[a]) / d[a],
+ * src/objects/rect.rs:49) against the hardware's IEEE division on n_pairs pseudo-random / adversarial operand pairs.
+ * violations[0]: results that are not bit-identical where exactness is promised; violations[1]: tiny-numerator
+ * results that would not be rejected by t_min = 0.001 (src/render.rs:19).  Both must be 0. */
+int fw_selftest_shared_division(int device, uint64_t n_pairs, uint64_t seed, uint64_t violations[2]);
+
 /* Microbenchmarks used by bench.py for the roofline denominators: dependent-free FP32 FMA rate (TFLOP/s) and
  * L2-resident streaming read bandwidth (GB/s) on `device`. */
 int fw_measure_peaks(int device, double* fp32_tflops, double* l2_gbs, int* sm_count, int* sm_clock_khz);

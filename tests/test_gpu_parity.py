@@ -36,6 +36,15 @@ def scenes():
         ns.close()
 
 
+def test_shared_division_is_ieee():
+    """The linear-scan kernels divide by a ray's direction components through a shared reciprocal
+    (intersect.cuh div_by): in its fast domain the quotient must be the IEEE one bit for bit, 2^32 operand pairs."""
+    from firework_b200.engine import selftest_shared_division
+    for seed in (1, 2):
+        bad, bad_tiny = selftest_shared_division(1 << 31, seed)
+        assert bad == 0 and bad_tiny == 0, (seed, bad, bad_tiny)
+
+
 @pytest.mark.parametrize("name", ALL_SCENES)
 def test_primary_rays_bit_exact(scenes, name):
     ns, orc = scenes(name)
