@@ -41,8 +41,8 @@ DEFAULT_WORKLOAD = "cornell_box"   # BASELINE.json configs[1]
 # static per-test operation / byte counts of the reference's routines
 F_NODE, F_SPHERE, F_RECT, F_TRI, F_CONIC, F_XROT, F_XTRANS, F_SHADE = 27, 40, 12, 60, 50, 33, 3, 45
 B_NODE, B_SPHERE, B_RECT, B_TRI, B_CONIC, B_XROT, B_XTRANS, B_RAY = 32, 16, 32, 48, 16, 112, 16, 64
-HBM_BYTES_PER_RAY = 160  # wavefront streams per extend+shade round: extend ray 32r + queue 4r + winner 16w + queue 4w;
-                         # shade queue 4r + ray 32r + winner 16r + ray 32w + atten 16w + queue 4w
+HBM_BYTES_PER_RAY = 176  # wavefront streams per extend + shade round (queues carry the records, all coalesced):
+                         # extend: ray 32 r + hit record 48 w;  shade: hit record 48 r + next ray 32 w + attenuation 16 w
 
 
 def read_scene_text(cfg):

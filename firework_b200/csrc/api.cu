@@ -9,6 +9,7 @@
 #include <fstream>
 #include <mutex>
 #include <sstream>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -19,6 +20,55 @@
 using namespace fw;
 
 static thread_local std::string g_last_error;
+
+// Pinned staging for equirect HDR maps (128 MiB as float4 at 4096 x 2048): fw_scene_set_hdr expands the caller's RGB
+// texels straight into it (one multi-threaded pass), fw_scene_commit copies from it into the CUDA array.  The buffers
+// are process-wide and grow-only; a scene holds one from set_hdr until its commit / destroy.
+struct HdrStaging {
+    float* p = nullptr;
+    size_t floats = 0;
+    bool in_use = false;
+};
+static std::mutex g_staging_mutex;
+static std::vector<HdrStaging*> g_staging;
+static HdrStaging* staging_acquire(size_t floats) {
+    std::lock_guard<std::mutex> lk(g_staging_mutex);
+    HdrStaging* best = nullptr;
+    for (HdrStaging* h : g_staging)
+        if (!h->in_use && (!best || h->floats > best->floats)) best = h;
+    if (!best) { best = new HdrStaging(); g_staging.push_back(best); }
+    if (best->floats < floats) {
+        if (best->p) cudaFreeHost(best->p);
+        best->p = nullptr; best->floats = 0;
+        if (cudaMallocHost(&best->p, floats * sizeof(float)) != cudaSuccess) {   // no device / no pinned memory:
+            cudaGetLastError();                                                // plain host memory still works
+            best->p = nullptr;
+            return nullptr;
+        }
+        best->floats = floats;
+    }
+    best->in_use = true;
+    return best;
+}
+static void staging_release(HdrStaging* h) {
+    if (!h) return;
+    std::lock_guard<std::mutex> lk(g_staging_mutex);
+    h->in_use = false;
+}
+static void expand_rgb_to_rgba(const float* rgb, float* rgba, size_t texels) {
+    unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (texels < (1u << 18)) nt = 1;
+    auto work = [=](size_t a, size_t b) {
+        for (size_t p = a; p < b; ++p) {
+            rgba[4 * p] = rgb[3 * p]; rgba[4 * p + 1] = rgb[3 * p + 1]; rgba[4 * p + 2] = rgb[3 * p + 2]; rgba[4 * p + 3] = 0.0f;
+        }
+    };
+    std::vector<std::thread> th;
+    size_t chunk = (texels + nt - 1) / nt;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, std::min(texels, t * chunk), std::min(texels, (t + 1) * chunk));
+    work(0, std::min(texels, chunk));
+    for (auto& t : th) t.join();
+}
 static int set_error(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
@@ -71,6 +121,7 @@ struct fw_scene {
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> texobjs;
     bool mat_present[MAT_NUM_QUEUES] = {false, false, false, false, false, false};
+    std::vector<HdrStaging*> hdr_staging;   // per asset: pinned RGBA copy of an HDR map (set_hdr .. commit)
     bool miss_is_zero = false;  // every escaping path contributes exactly 0: the miss kernel is not launched
     RenderCtx* ctx = nullptr;  // render-time state, borrowed from the per-device cache at commit
     size_t batch_paths = 0;    // 0 = default
@@ -211,6 +262,7 @@ int fw_scene_from_file(const char* path, fw_scene** out) {
 }
 void fw_scene_destroy(fw_scene* sc) {
     if (!sc) return;
+    for (HdrStaging* h : sc->hdr_staging) staging_release(h);
     release_device(sc);
     delete sc;
 }
@@ -242,7 +294,17 @@ int fw_scene_set_hdr(fw_scene* sc, int i, uint32_t w, uint32_t h, const float* r
     if (a.kind != 1) return set_error(FW_ERR_ARG, "asset is not an HDR map");
     if (sc->committed) return set_error(FW_ERR_STATE, "scene already committed");
     a.w = w; a.h = h;
-    a.rgb.assign(rgb, rgb + (size_t)w * h * 3);
+    const size_t texels = (size_t)w * h;
+    sc->hdr_staging.resize(sc->desc.assets.size(), nullptr);
+    if (sc->hdr_staging[i]) { staging_release(sc->hdr_staging[i]); sc->hdr_staging[i] = nullptr; }
+    HdrStaging* st = staging_acquire(texels * 4);
+    if (st) {
+        expand_rgb_to_rgba(rgb, st->p, texels);
+        sc->hdr_staging[i] = st;
+        a.rgb.clear();
+    } else {
+        a.rgb.assign(rgb, rgb + texels * 3);
+    }
     a.provided = true;
     return FW_OK;
 }
@@ -331,12 +393,18 @@ int fw_scene_commit(fw_scene* sc, int device) {
             if ((rc = make_texture(sc, a.rgba.data(), a.w, a.h, false, &images[i].tex)) != FW_OK) return rc;
             images[i].w = a.w; images[i].h = a.h;
         } else {
-            std::vector<float> rgba((size_t)a.w * a.h * 4);
-            for (size_t p = 0; p < (size_t)a.w * a.h; ++p) {
-                rgba[4 * p] = a.rgb[3 * p]; rgba[4 * p + 1] = a.rgb[3 * p + 1]; rgba[4 * p + 2] = a.rgb[3 * p + 2]; rgba[4 * p + 3] = 0.0f;
-            }
             cudaTextureObject_t t;
-            if ((rc = make_texture(sc, rgba.data(), a.w, a.h, true, &t)) != FW_OK) return rc;
+            HdrStaging* hs = i < sc->hdr_staging.size() ? sc->hdr_staging[i] : nullptr;
+            if (hs) {
+                rc = make_texture(sc, hs->p, a.w, a.h, true, &t);
+                staging_release(hs);
+                sc->hdr_staging[i] = nullptr;
+                if (rc != FW_OK) return rc;
+            } else {
+                std::vector<float> rgba((size_t)a.w * a.h * 4);
+                expand_rgb_to_rgba(a.rgb.data(), rgba.data(), (size_t)a.w * a.h);
+                if ((rc = make_texture(sc, rgba.data(), a.w, a.h, true, &t)) != FW_OK) return rc;
+            }
             if ((int)i == sc->desc.env_asset) { D.env.tex = t; D.env.w = a.w; D.env.h = a.h; }
         }
     }
