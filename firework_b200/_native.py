@@ -42,7 +42,8 @@ EXPORTS = [
     "fw_scene_num_nodes", "fw_scene_device_bytes", "fw_scene_top_leaf_order", "fw_scene_object_aabb", "fw_scene_mesh_leaf_order", "fw_scene_linear_program", "fw_render",
     "fw_render_accumulate_device", "fw_resolve_device", "fw_primary_rays", "fw_first_hit", "fw_scatter_step",
     "fw_env_sample", "fw_texture_sample", "fw_material_texture", "fw_camera", "fw_last_error", "fw_version",
-    "fw_device_count", "fw_measure_peaks", "fw_selftest_shared_division", "fw_set_profiling", "fw_set_batch_paths", "fw_release_cached_memory",
+    "fw_device_count", "fw_measure_peaks", "fw_selftest_shared_division", "fw_obj_load", "fw_obj_num_models",
+    "fw_obj_model_name", "fw_obj_model_sizes", "fw_obj_model_copy", "fw_obj_destroy", "fw_hdr_load", "fw_hdr_free", "fw_set_profiling", "fw_set_batch_paths", "fw_release_cached_memory",
 ]
 
 _lib = None
@@ -62,6 +63,17 @@ def lib():
         L.fw_scene_from_yaml.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.fw_scene_from_file.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.fw_scene_destroy.argtypes = [C.c_void_p]
+        L.fw_obj_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.fw_obj_num_models.argtypes = [C.c_void_p]
+        L.fw_obj_model_name.argtypes = [C.c_void_p, C.c_int]
+        L.fw_obj_model_name.restype = C.c_char_p
+        L.fw_obj_model_sizes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.fw_obj_model_copy.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fw_obj_destroy.argtypes = [C.c_void_p]
+        L.fw_obj_destroy.restype = None
+        L.fw_hdr_load.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.POINTER(C.c_float))]
+        L.fw_hdr_free.argtypes = [C.POINTER(C.c_float)]
+        L.fw_hdr_free.restype = None
         L.fw_scene_destroy.restype = None
         for name in ("fw_scene_num_assets", "fw_scene_num_objects", "fw_scene_num_nodes"):
             getattr(L, name).argtypes = [C.c_void_p]

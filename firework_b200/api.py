@@ -103,20 +103,27 @@ class Rotor3:
         return Rotor3()
 
     @staticmethod
+    def _from_angle_plane(angle, plane):
+        # ultraviolet 0.5.1 Rotor3::from_angle_plane: (sin, cos) = (angle * 0.5).sin_cos(); Rotor3::new(cos, plane * -sin).
+        # libm's sinf / cosf are correctly rounded: evaluate in f64 and round once.  `plane * -sin` keeps the sign of
+        # its zero components (0 * -sin = -0.0 for sin > 0), as the reference's scenes/teapot.yml shows.
+        half = F(F(angle) * F(0.5))
+        sin, cos = F(math.sin(float(half))), F(math.cos(float(half)))
+        bv = [float(F(c) * -sin) for c in plane]
+        return Rotor3(float(cos), bv[0], bv[1], bv[2])
+
+    @staticmethod
     def from_rotation_xz(angle):
-        # {s: cos(a/2), xz: -sin(a/2)} — pinned numerically by scenes/suzanne.yml (a = -30 rad).
-        half = F(angle) / F(2.0)
-        return Rotor3(f32(np.cos(half)), 0.0, f32(-np.sin(half)), 0.0)
+        # pinned numerically by scenes/suzanne.yml (a = -30 rad) and scenes/teapot.yml (a = 90 rad)
+        return Rotor3._from_angle_plane(angle, (0.0, 1.0, 0.0))
 
     @staticmethod
     def from_rotation_xy(angle):
-        half = F(angle) / F(2.0)
-        return Rotor3(f32(np.cos(half)), f32(-np.sin(half)), 0.0, 0.0)
+        return Rotor3._from_angle_plane(angle, (1.0, 0.0, 0.0))
 
     @staticmethod
     def from_rotation_yz(angle):
-        half = F(angle) / F(2.0)
-        return Rotor3(f32(np.cos(half)), 0.0, 0.0, f32(-np.sin(half)))
+        return Rotor3._from_angle_plane(angle, (0.0, 0.0, 1.0))
 
     def to_dict(self):
         return {"s": f32(self.s), "bv": {"xy": f32(self.xy), "xz": f32(self.xz), "yz": f32(self.yz)}}
@@ -285,6 +292,20 @@ class HdrEnvironment:
 # ---------------------------------------------------------------------------------------------------
 # shapes (src/objects/*.rs)
 # ---------------------------------------------------------------------------------------------------
+def add_obj(scene, file_name, material, with_normals=False, rotate=None):
+    """The `add_obj` helper of examples/suzanne.rs:15-51 (with_normals=False) and examples/teapot.rs:17-64
+    (with_normals=True, rotate=Rotor3.from_rotation_xz(90.)): one TriangleMesh render object per OBJ model."""
+    from .assets import load_obj
+    ids = []
+    for m in load_obj(str(file_name)):
+        normals = m["normals"] if with_normals else None
+        obj = RenderObject.new(TriangleMesh(m["positions"], m["indices"], normals, None, material))
+        if rotate is not None:
+            obj = obj.rotate(rotate)
+        ids.append(scene.add_object(obj))
+    return ids
+
+
 class Sphere:
     def __init__(self, radius, material):
         self.radius, self.material = f32(radius), int(material)

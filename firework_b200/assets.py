@@ -56,7 +56,47 @@ def load_asset(path: str, kind: str, asset_dir: str | None = None, registry: dic
             if kind == "hdr":
                 if c.endswith(".npy"):
                     return np.ascontiguousarray(np.load(c), dtype=np.float32)
-                raise ValueError(f"Radiance .hdr decoding is not implemented (asset {c}); provide a .npy")
+                return load_hdr(c)
             from PIL import Image
             return np.ascontiguousarray(np.asarray(Image.open(c).convert("RGBA")), dtype=np.uint8)
     raise FileNotFoundError(f"asset {path!r} not found (searched {cands})")
+
+
+def load_hdr(path: str) -> np.ndarray:
+    """Radiance RGBE .hdr -> (H, W, 3) fp32, row 0 = top — the native decoder (fw_hdr_load), which restates
+    image 0.23.9 `HdrDecoder::read_image_hdr` (examples/hdri_test.rs:45-67)."""
+    import ctypes as C
+
+    from . import _native as N
+    L = N.lib()
+    w, h, p = C.c_uint32(), C.c_uint32(), C.POINTER(C.c_float)()
+    N.check(L.fw_hdr_load(path.encode(), C.byref(w), C.byref(h), C.byref(p)))
+    try:
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
+    finally:
+        L.fw_hdr_free(p)
+
+
+def load_obj(path: str):
+    """Wavefront OBJ -> list of models {name, positions (N,3), normals (N,3)|None, texcoords (N,2)|None, indices (M,)}:
+    the native loader (fw_obj_load), which restates tobj 1.0.0 `load_obj` (examples/suzanne.rs:19)."""
+    import ctypes as C
+
+    from . import _native as N
+    L = N.lib()
+    h = C.c_void_p()
+    N.check(L.fw_obj_load(path.encode(), C.byref(h)))
+    try:
+        models = []
+        for m in range(L.fw_obj_num_models(h)):
+            sz = np.zeros(4, np.uint32)
+            N.check(L.fw_obj_model_sizes(h, m, N.ptr(sz)))
+            pos, nrm, tex = (np.zeros(int(n), np.float32) for n in sz[:3])
+            idx = np.zeros(int(sz[3]), np.uint32)
+            N.check(L.fw_obj_model_copy(h, m, N.ptr(pos), N.ptr(nrm), N.ptr(tex), N.ptr(idx)))
+            models.append({"name": L.fw_obj_model_name(h, m).decode(), "positions": pos.reshape(-1, 3),
+                           "normals": nrm.reshape(-1, 3) if len(nrm) else None,
+                           "texcoords": tex.reshape(-1, 2) if len(tex) else None, "indices": idx})
+        return models
+    finally:
+        L.fw_obj_destroy(h)

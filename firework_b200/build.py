@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfirework_b200.so")
-SOURCES = ["api.cu", "scene_host.cpp", "yaml_lite.cpp"]
+SOURCES = ["api.cu", "scene_host.cpp", "yaml_lite.cpp", "formats.cpp"]
 HEADERS = ["fw_types.h", "scene_host.h", "yaml_lite.h", "device_math.cuh", "intersect.cuh", "shade.cuh",
            "wavefront.cuh", os.path.join("..", "..", "include", "firework_b200.h")]
 

@@ -73,6 +73,7 @@ static int set_error(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
+int fw::set_last_error(int code, const std::string& msg) { return set_error(code, msg); }
 #define FW_CUDA(call)                                                                                         \
     do {                                                                                                      \
         cudaError_t e__ = (call);                                                                             \

@@ -109,4 +109,7 @@ struct RenderParamsHost {
 };
 CameraRec make_camera(const RenderParamsHost& p);
 
+// Records the message fw_last_error() returns on this thread and passes `code` through (api.cu).
+int set_last_error(int code, const std::string& msg);
+
 }  // namespace fw

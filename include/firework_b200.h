@@ -135,6 +135,22 @@ int fw_camera(const fw_params* params, float out24[24]);        /* camera.rs:74-
 const char* fw_last_error(void);
 const char* fw_version(void);
 int fw_device_count(void);
+/* ---- asset ingestion in front of the path (what the reference's examples do with third-party crates) --------
+ * fw_obj_load  : Wavefront OBJ -> indexed triangle models, as tobj 1.0.0 `load_obj` (examples/suzanne.rs:15-51,
+ *                examples/teapot.rs:17-64): one model per `o` / `g` group, fan triangulation, one vertex per distinct
+ *                v/vt/vn triple in order of first use.  The arrays feed TriangleMesh::new (src/objects/mesh.rs:36-72).
+ * fw_hdr_load  : Radiance RGBE .hdr -> fp32 RGB, row 0 = top, as image 0.23.9 `HdrDecoder::read_image_hdr`
+ *                (examples/hdri_test.rs:45-67); the result feeds fw_scene_set_hdr.  Free with fw_hdr_free. */
+typedef struct fw_obj fw_obj;
+int fw_obj_load(const char* path, fw_obj** out);
+int fw_obj_num_models(const fw_obj* obj);
+const char* fw_obj_model_name(const fw_obj* obj, int model);
+int fw_obj_model_sizes(const fw_obj* obj, int model, uint32_t sizes[4]);   /* floats: positions, normals, texcoords; indices */
+int fw_obj_model_copy(const fw_obj* obj, int model, float* positions, float* normals, float* texcoords, uint32_t* indices);
+void fw_obj_destroy(fw_obj* obj);
+int fw_hdr_load(const char* path, uint32_t* width, uint32_t* height, float** rgb);
+void fw_hdr_free(float* rgb);
+
 /* Self-test of the shared-reciprocal division used by the linear-scan kernels (t = (k - o[a]) / d[a],
  * src/objects/rect.rs:49) against the hardware's IEEE division on n_pairs pseudo-random / adversarial operand pairs.
  * violations[0]: results that are not bit-identical where exactness is promised; violations[1]: tiny-numerator
