@@ -271,21 +271,29 @@ def test_device_accumulate_and_resolve_via_torch(scenes):
     assert np.array_equal(img1, rgb)
 
 
-@pytest.mark.parametrize("name,w,h", [("cornell_box", 64, 64), ("random_spheres", 96, 54)])
+@pytest.mark.parametrize("name,w,h", [("cornell_box", 64, 64), ("random_spheres", 96, 54), ("suzanne", 96, 54), ("teapot", 96, 54),
+                                      ("hdri_test", 100, 50), ("earth", 64, 64), ("part2_all", 96, 54)])
 def test_converged_image_gate(scenes, name, w, h):
-    """Gate 3 at reduced resolution (camera framing is resolution independent, camera.rs:89-95): 4096 spp."""
+    """Gate 3 at reduced resolution (camera framing is resolution independent, camera.rs:89-95): 4096 spp, every
+    BASELINE.json config."""
     ns, orc = scenes(name)
     p = params_for(name, w, h, 4096, seed=2)
     grgb, gsum, _ = ns.render(p)
     orgb, osum, _ = orc.render(p)
     assert psnr_u8(grgb, orgb) >= 40.0
     gm, om = gsum / 4096.0, osum / 4096.0
-    assert abs(gm.mean() - om.mean()) / om.mean() < 0.01
-    mre = np.mean(np.abs(gm - om) / np.maximum(om, 1e-2))
+    ok = np.isfinite(om) & np.isfinite(gm)          # part2_all: a NaN-direction path makes a pixel NaN on both sides
+    assert np.array_equal(np.isfinite(om), np.isfinite(gm)) and ok.mean() > 0.999
+    assert abs(gm[ok].mean() - om[ok].mean()) / abs(om[ok].mean()) < 0.01
+    mre = np.mean(np.abs(gm[ok] - om[ok]) / np.maximum(np.abs(om[ok]), 1e-2))
     assert mre < 0.01, mre
-    # statistically independent check: a different seed on the GPU must still agree in the mean
+    # statistically independent check: a different seed on the GPU must still agree in the mean (Monte-Carlo noise
+    # of the no-NEE estimator sets the tolerance: small bright lights converge slowly)
     _, gsum2, _ = ns.render(params_for(name, w, h, 4096, seed=77))
-    assert abs((gsum2 / 4096.0).mean() - om.mean()) / om.mean() < 0.02
+    g2 = gsum2 / 4096.0
+    ok2 = ok & np.isfinite(g2)
+    tol = 0.02 if name in ("cornell_box", "random_spheres", "earth", "hdri_test") else 0.05
+    assert abs(g2[ok2].mean() - om[ok2].mean()) / abs(om[ok2].mean()) < tol
 
 
 @pytest.mark.parametrize("name,spp", [("random_spheres", 32), ("cornell_box", 1024), ("part2_all", 2)])
