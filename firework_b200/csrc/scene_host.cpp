@@ -464,11 +464,75 @@ bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& er
     // child's box contains the grandchild's, and the slab arithmetic (aabb.rs:38-47) is monotonic in the box
     // planes, so "grandchild box hit" implies "child box hit" bit for bit.
     auto leaf_code = [](const BuildNode& n) { return ~(n.first * 2 + (n.count - 1)); };  // items [first, first+count)
-    const BuildNode& rootn = b.nodes[root];
-    out.root_box = rootn.box;
-    if (rootn.count > 0) {
-        out.root_code = leaf_code(rootn);
+    out.root_box = b.nodes[root].box;
+    if (b.nodes[root].count > 0) {
+        out.root_code = leaf_code(b.nodes[root]);
         return true;
+    }
+    // Interior re-clustering.  Which items a ray tests is decided by the LEAF boxes alone: a leaf (bvh.rs Leaf /
+    // DoubleLeaf, with the reference's box for it) is reached iff its own box test passes, because every ancestor's
+    // box contains it and the slab arithmetic is monotonic in the box planes.  Any hierarchy that conservatively
+    // bounds those leaves therefore yields the reference's candidate set, and the (t, DFS rank) merge rule does not
+    // depend on visiting order.  The reference's tree (median split on a cycling axis) supplies the leaves, their
+    // boxes and their DFS ranks; the interior nodes above them are rebuilt with a surface-area heuristic, which
+    // roughly halves the boxes a ray has to test (FW_BVH_SAH=0 keeps the reference's interior).
+    static const bool use_sah = [] { const char* e = getenv("FW_BVH_SAH"); return !e || atoi(e) != 0; }();
+    if (use_sah) {
+        std::vector<int> leaves;
+        for (int i = 0; i < (int)b.nodes.size(); ++i)
+            if (b.nodes[i].count > 0) leaves.push_back(i);   // creation order == DFS order
+        b.nodes.reserve(b.nodes.size() + leaves.size());
+        auto area = [](const Box& x) {
+            double dx = (double)x.mx.x - x.mn.x, dy = (double)x.mx.y - x.mn.y, dz = (double)x.mx.z - x.mn.z;
+            dx = std::max(dx, 0.0); dy = std::max(dy, 0.0); dz = std::max(dz, 0.0);
+            return dx * dy + dy * dz + dz * dx;
+        };
+        auto center = [&](int id, int a) {
+            const Box& x = b.nodes[id].box;
+            return a == 0 ? 0.5 * ((double)x.mn.x + x.mx.x) : a == 1 ? 0.5 * ((double)x.mn.y + x.mx.y) : 0.5 * ((double)x.mn.z + x.mx.z);
+        };
+        constexpr int kMaxDepth = 22;   // binary levels below the root: keeps the traversal stack within FW_STACK
+        std::function<int(int, int, int)> sah = [&](int lo, int n, int depth) -> int {
+            if (n == 1) return leaves[lo];
+            int best_axis = -1, best_k = n / 2;
+            double best_cost = INFINITY;
+            int levels_needed = 0;
+            while ((1 << levels_needed) < n) ++levels_needed;
+            const bool balanced = depth + levels_needed >= kMaxDepth;
+            std::vector<int> tmp(leaves.begin() + lo, leaves.begin() + lo + n), best_order;
+            std::vector<double> right_area(n);
+            for (int a = 0; a < 3; ++a) {
+                std::stable_sort(tmp.begin(), tmp.end(), [&](int p, int q) { return center(p, a) < center(q, a); });
+                Box acc = b.nodes[tmp[n - 1]].box;
+                for (int i = n - 1; i > 0; --i) {
+                    acc = box_expand(acc, b.nodes[tmp[i]].box);
+                    right_area[i] = area(acc);
+                }
+                acc = b.nodes[tmp[0]].box;
+                int items_left = 0, items_total = 0;
+                for (int i = 0; i < n; ++i) items_total += b.nodes[tmp[i]].count;
+                for (int k = 1; k < n; ++k) {   // left = tmp[0..k), right = tmp[k..n)
+                    acc = box_expand(acc, b.nodes[tmp[k - 1]].box);
+                    items_left += b.nodes[tmp[k - 1]].count;
+                    if (balanced && k != n / 2) continue;
+                    double cost = area(acc) * items_left + right_area[k] * (items_total - items_left);
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_k = k; best_order = tmp; }
+                }
+            }
+            if (best_axis < 0) { best_order = tmp; best_k = n / 2; }   // non-finite areas: any split is valid
+            std::copy(best_order.begin(), best_order.end(), leaves.begin() + lo);
+            int l = sah(lo, best_k, depth + 1);
+            int r = sah(lo + best_k, n - best_k, depth + 1);
+            int id = (int)b.nodes.size();
+            b.nodes.emplace_back();
+            b.nodes[id].depth = depth;
+            b.nodes[id].left = l;
+            b.nodes[id].right = r;
+            b.nodes[id].box = box_expand(b.nodes[l].box, b.nodes[r].box);
+            b.nodes[id].unbounded = b.nodes[l].unbounded || b.nodes[r].unbounded;
+            return id;
+        };
+        root = sah(0, (int)leaves.size(), 0);
     }
     out.root_code = 0;
     struct Pending { int bn; int wide; int depth; };
@@ -482,10 +546,32 @@ bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& er
         out.wide_depth = std::max(out.wide_depth, cur.depth);
         const BuildNode& n = b.nodes[cur.bn];
         int kids[4], nk = 0;
-        for (int side : {n.left, n.right}) {
-            const BuildNode& c = b.nodes[side];
-            if (c.count > 0) kids[nk++] = side;
-            else { kids[nk++] = c.left; kids[nk++] = c.right; }
+        if (use_sah) {
+            // greedy collapse: open the interior child with the largest box until the four slots are used
+            auto half_area = [](const Box& x) {
+                double dx = std::max((double)x.mx.x - x.mn.x, 0.0), dy = std::max((double)x.mx.y - x.mn.y, 0.0), dz = std::max((double)x.mx.z - x.mn.z, 0.0);
+                return dx * dy + dy * dz + dz * dx;
+            };
+            kids[nk++] = n.left; kids[nk++] = n.right;
+            while (nk < 4) {
+                int pick = -1;
+                double best = -1.0;
+                for (int k = 0; k < nk; ++k)
+                    if (b.nodes[kids[k]].count == 0) {
+                        double a = half_area(b.nodes[kids[k]].box);
+                        if (!(a <= best)) { best = a; pick = k; }
+                    }
+                if (pick < 0) break;
+                int open = kids[pick];
+                kids[pick] = b.nodes[open].left;
+                kids[nk++] = b.nodes[open].right;
+            }
+        } else {
+            for (int side : {n.left, n.right}) {
+                const BuildNode& c = b.nodes[side];
+                if (c.count > 0) kids[nk++] = side;
+                else { kids[nk++] = c.left; kids[nk++] = c.right; }
+            }
         }
         float lo[3][4], hi[3][4];
         int code[4], flag[4];
@@ -846,7 +932,7 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
     FlatBVH top;
     if (!build_bvh(out.obj_aabb, top, err, &obj_unbounded)) return false;
     // traversal stack: up to 3 deferred siblings per wide level, on both levels, plus EXIT / ENTER markers
-    if (3 * (top.wide_depth + max_mesh_wide_depth) + 8 > 64) {
+    if (3 * (top.wide_depth + max_mesh_wide_depth) + 8 > 96) {   // FW_STACK (intersect.cuh)
         err = "BVH deeper than the traversal stack";
         return false;
     }
