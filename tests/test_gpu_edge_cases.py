@@ -157,3 +157,49 @@ def test_zero_samples_and_bad_arguments():
     with pytest.raises(FireworkError):
         ns.render(bad)
     ns.close()
+
+
+def _linear_scene(n_spheres):
+    """A linear-scan scene: n translated spheres + a ground rect + a Rect3d with canonical faces + a rotated one."""
+    s = _base_scene()
+    m = s.add_material(LambertianMat.with_color(Vec3(0.6, 0.3, 0.2)))
+    g = s.add_material(MetalMat(Vec3(0.8, 0.8, 0.8), 0.1))
+    rng = np.random.default_rng(9)
+    for i in range(n_spheres):
+        x, z = rng.uniform(-3.0, 3.0, 2)
+        s.add_object(RenderObject.new(Sphere(0.25, m if i % 2 else g)).position(float(x), 0.25, float(z)))
+    s.add_object(RenderObject.new(XZRect(-6.0, 6.0, -6.0, 6.0, 0.0, m)))
+    s.add_object(RenderObject.new(Rect3d.with_size(Vec3(0.8, 1.2, 0.8), g)).position(-1.0, 0.0, 1.0))
+    s.add_object(RenderObject.new(Rect3d.with_size(Vec3(0.6, 0.6, 0.6), m)).rotate(Rotor3.from_rotation_xz(0.6)).position(1.2, 0.0, 0.5))
+    return s
+
+
+def test_linear_program_and_object_loop_kernels_agree(monkeypatch):
+    """Linear-scan scenes run the LinProgram kernels when the program fits kernel-parameter space, and the object-loop
+    kernels otherwise (or with FW_LINEAR_PROGRAM=0).  Both must give the oracle's result, and each other's, bit for bit."""
+    small = _linear_scene(6)
+    ns = NativeScene(small.to_yaml())
+    words = ns.linear_program()
+    assert 0 < len(words) <= 160
+    p = _renderer(64, 40, 4, False).params()
+    _, sum_prog, _ = ns.render(p)
+    o, d = ns.primary_rays(p, 0)
+    hit_prog = ns.first_hit(o, d, False, seed=3)
+    ns.close()
+    monkeypatch.setenv("FW_LINEAR_PROGRAM", "0")
+    ns2 = NativeScene(small.to_yaml())
+    _, sum_loop, _ = ns2.render(p)
+    hit_loop = ns2.first_hit(o, d, False, seed=3)
+    ns2.close()
+    monkeypatch.delenv("FW_LINEAR_PROGRAM")
+    assert np.array_equal(sum_prog, sum_loop, equal_nan=True)
+    for k in ("obj", "prim", "material", "t", "point", "normal"):
+        assert np.array_equal(hit_prog[k], hit_loop[k], equal_nan=True), k
+    _compare(small, 64, 40, 4, False)
+    # too many items for kernel-parameter space: the object-loop kernels take over by themselves
+    big = _linear_scene(120)
+    nb = NativeScene(big.to_yaml(), commit=False)
+    nb.build_host()
+    assert len(nb.linear_program()) > 160
+    nb.close()
+    _compare(big, 48, 30, 2, False)
