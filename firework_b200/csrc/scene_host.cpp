@@ -643,6 +643,41 @@ static Box triangle_box(V3 p0, V3 p1, V3 p2) {
 }
 }  // namespace
 
+// Rect3d helpers (see the device-record comment in flatten_scene).  `s` is the Rect3d's ShapeRec: faces are
+// desc.shapes[s.i0 .. s.i0 + s.i1), each (min1, min2, max1, max2, k) with its plane in i0 & 3 (0 XY, 1 XZ, 2 YZ).
+static bool rect3d_canonical(const SceneDesc& desc, const ShapeRec& s, float lo[3], float hi[3]) {
+    auto bits_eq = [](float a, float b) { return memcmp(&a, &b, 4) == 0; };
+    if (s.i1 != 6) return false;
+    const ShapeRec* f = &desc.shapes[s.i0];
+    static const int planes[6] = {0, 0, 1, 1, 2, 2};
+    for (int k = 0; k < 6; ++k)
+        if (f[k].kind != SH_RECT || (f[k].i0 & 3) != planes[k]) return false;
+    lo[0] = f[0].f[0]; lo[1] = f[0].f[1]; hi[0] = f[0].f[2]; hi[1] = f[0].f[3]; hi[2] = f[0].f[4]; lo[2] = f[1].f[4];
+    const float exp[6][5] = {{lo[0], lo[1], hi[0], hi[1], hi[2]}, {lo[0], lo[1], hi[0], hi[1], lo[2]},
+                             {lo[0], lo[2], hi[0], hi[2], hi[1]}, {lo[0], lo[2], hi[0], hi[2], lo[1]},
+                             {lo[1], lo[2], hi[1], hi[2], hi[0]}, {lo[1], lo[2], hi[1], hi[2], lo[0]}};
+    for (int k = 0; k < 6; ++k)
+        for (int c = 0; c < 5; ++c)
+            if (!bits_eq(f[k].f[c], exp[k][c])) return false;
+    return true;
+}
+static void rect3d_padded_box(const SceneDesc& desc, const ShapeRec& s, float lo[3], float hi[3]) {
+    for (int a = 0; a < 3; ++a) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+    static const int A1[3] = {0, 0, 1}, A2[3] = {1, 2, 2}, AK[3] = {2, 1, 0};
+    for (int f = 0; f < s.i1; ++f) {
+        const ShapeRec& r = desc.shapes[s.i0 + f];
+        int p = r.i0 & 3;
+        lo[A1[p]] = fminf(lo[A1[p]], r.f[0]); hi[A1[p]] = fmaxf(hi[A1[p]], r.f[2]);
+        lo[A2[p]] = fminf(lo[A2[p]], r.f[1]); hi[A2[p]] = fmaxf(hi[A2[p]], r.f[3]);
+        lo[AK[p]] = fminf(lo[AK[p]], r.f[4]); hi[AK[p]] = fmaxf(hi[AK[p]], r.f[4]);
+    }
+    float ext = 0.0f;
+    for (int a = 0; a < 3; ++a) ext = fmaxf(ext, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+    float pad = 1e-3f * ext + 1e-4f;
+    if (!(ext < INFINITY)) pad = 0.0f;  // no faces / non-finite: the inverted or infinite box decides
+    for (int a = 0; a < 3; ++a) { lo[a] -= pad; hi[a] += pad; }
+}
+
 bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
     out = HostFlat();
     if (desc.objects.empty()) {
@@ -652,27 +687,26 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
     out.shapes = desc.shapes;
     out.mats = desc.mats;
     out.texs = desc.texs;
-    // Rect3d: the device copy carries a PADDED box around the union of its faces in f[0..5] (lo xyz, hi xyz).
-    // The kernels use it as a conservative pre-test before the six face tests (rect3d.rs:89-100): a face can only
-    // be hit inside that box, and the padding (1e-3 of the extent + 1e-4) dwarfs every rounding difference
-    // between the slab arithmetic and the face test, so skipping the faces when the box is missed never changes
-    // a result.  (pos / size themselves are only needed for the object's bounding box, computed below from desc.)
+    // Rect3d device records.
+    //  * canonical (the six faces Rect3d::new builds, rect3d.rs:18-80, all sharing lo / hi): f[0..5] = lo xyz, hi xyz
+    //    exactly, f[7] = 1 — the kernels run the six face tests straight-line from those six numbers, without loading
+    //    the face records;
+    //  * anything else (a deserialised Rect3d may hold arbitrary faces): f[0..5] = a PADDED box around the union of
+    //    the faces, f[7] = 0.  The kernels use it as a conservative pre-test before the face tests (rect3d.rs:89-100):
+    //    a face can only be hit inside that box, and the padding (1e-3 of the extent + 1e-4) dwarfs every rounding
+    //    difference between the slab arithmetic and the face test.
+    // (pos / size themselves are only needed for the object's bounding box, computed below from desc.)
     for (ShapeRec& s : out.shapes) {
         if (s.kind != SH_RECT3D) continue;
-        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        static const int A1[3] = {0, 0, 1}, A2[3] = {1, 2, 2}, AK[3] = {2, 1, 0};
-        for (int f = 0; f < s.i1; ++f) {
-            const ShapeRec& r = desc.shapes[s.i0 + f];
-            int p = r.i0 & 3;
-            lo[A1[p]] = fminf(lo[A1[p]], r.f[0]); hi[A1[p]] = fmaxf(hi[A1[p]], r.f[2]);
-            lo[A2[p]] = fminf(lo[A2[p]], r.f[1]); hi[A2[p]] = fmaxf(hi[A2[p]], r.f[3]);
-            lo[AK[p]] = fminf(lo[AK[p]], r.f[4]); hi[AK[p]] = fmaxf(hi[AK[p]], r.f[4]);
+        float lo[3], hi[3];
+        if (rect3d_canonical(desc, s, lo, hi)) {
+            for (int a = 0; a < 3; ++a) { s.f[a] = lo[a]; s.f[3 + a] = hi[a]; }
+            s.f[6] = 0.0f; s.f[7] = 1.0f;
+            continue;
         }
-        float ext = 0.0f;
-        for (int a = 0; a < 3; ++a) ext = fmaxf(ext, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
-        float pad = 1e-3f * ext + 1e-4f;
-        if (!(ext < INFINITY)) pad = 0.0f;  // no faces / non-finite: the inverted or infinite box decides
-        for (int a = 0; a < 3; ++a) { s.f[a] = lo[a] - pad; s.f[3 + a] = hi[a] + pad; }
+        rect3d_padded_box(desc, s, lo, hi);
+        for (int a = 0; a < 3; ++a) { s.f[a] = lo[a]; s.f[3 + a] = hi[a]; }
+        s.f[6] = 0.0f; s.f[7] = 0.0f;
     }
     {
         // uv is read only by ImageTexture::sample (texture.rs:296-309); checker forwards it to its children
@@ -898,25 +932,15 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
             } else {
                 // Rect3d: the six canonical faces of Rect3d::new (rect3d.rs:18-80) collapse into one BOX6 item
                 const ShapeRec* f = &desc.shapes[s.i0];
-                bool canon = s.i1 == 6;
-                static const int planes[6] = {0, 0, 1, 1, 2, 2};
-                for (int k = 0; canon && k < 6; ++k) canon = (f[k].kind == SH_RECT) && ((f[k].i0 & 3) == planes[k]);
-                float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-                if (canon) {
-                    lo[0] = f[0].f[0]; lo[1] = f[0].f[1]; hi[0] = f[0].f[2]; hi[1] = f[0].f[3]; hi[2] = f[0].f[4]; lo[2] = f[1].f[4];
-                    // face k: (min1, min2, max1, max2, k) expected from lo / hi
-                    const float exp[6][5] = {{lo[0], lo[1], hi[0], hi[1], hi[2]}, {lo[0], lo[1], hi[0], hi[1], lo[2]},
-                                             {lo[0], lo[2], hi[0], hi[2], hi[1]}, {lo[0], lo[2], hi[0], hi[2], lo[1]},
-                                             {lo[1], lo[2], hi[1], hi[2], hi[0]}, {lo[1], lo[2], hi[1], hi[2], lo[0]}};
-                    for (int k = 0; canon && k < 6; ++k)
-                        for (int c = 0; canon && c < 5; ++c) canon = bits_eq(f[k].f[c], exp[k][c]);
-                }
+                float lo[3], hi[3];
                 out.lin_rect_tests += s.i1;
-                if (canon) {
+                if (rect3d_canonical(desc, desc.shapes[o.shape], lo, hi)) {
+                    float plo[3], phi[3];
+                    rect3d_padded_box(desc, desc.shapes[o.shape], plo, phi);
                     W.push_back(float4{lo[0], as_float(LIN_BOX6), as_float((int)i), lo[1]});
                     W.push_back(float4{lo[2], hi[0], hi[1], hi[2]});
-                    W.push_back(float4{s.f[0], s.f[1], s.f[2], s.f[3]});
-                    W.push_back(float4{s.f[4], s.f[5], 0, 0});
+                    W.push_back(float4{plo[0], plo[1], plo[2], phi[0]});
+                    W.push_back(float4{phi[1], phi[2], 0, 0});
                 } else {
                     for (int k = 0; k < s.i1; ++k) {
                         W.push_back(float4{f[k].f[4], as_float(LIN_RECT | ((f[k].i0 & 3) << 8)), as_float((int)i), as_float(k)});
