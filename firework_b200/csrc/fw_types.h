@@ -93,13 +93,14 @@ struct EnvRec {
     cudaTextureObject_t tex;  // HdrEnvironment: float4 point-sampled
 };
 
-// BVH: the reference's binary median-split tree (bvh.rs:21-71), collapsed two levels at a time into 4-wide nodes.
-// Wide node = 8 x float4 (128 B, one cache line):
+// BVH: the LEAVES are those of the reference's binary median-split tree (bvh.rs:21-71: same items, same boxes, same
+// DFS order); the hierarchy above them is rebuilt with a surface-area heuristic and collapsed into 4-wide nodes
+// (scene_host.cpp build_bvh explains why that cannot change which items a ray tests).
+// Wide node = 8 x float4 (128 B, one cache line, 128-byte aligned):
 //   [0..2] child min x / y / z (one lane per child)   [3..5] child max x / y / z
 //   [6]    child codes (int bits):  >= 0 wide node index;  < 0 leaf: p = ~code, items [p >> 1, (p >> 1) + (p & 1) + 1)
 //          of the tree's item list (1 or 2 items: bvh.rs Leaf / DoubleLeaf); empty slots carry an inverted box
-//   [7]    child flags (int bits): bit 0 = some item below has a box that does not bound its geometry (Disk)
-//          -> that child is never distance-culled
+//   [7]    host-side bookkeeping only (which children hold a Disk); the kernels do not read it
 struct DeviceScene {
     const float4* nodes;       // wide nodes of all trees (top-level tree first)
     float4 top_lo, top_hi;     // the top-level root's box; top_lo.w = asfloat(root code)
