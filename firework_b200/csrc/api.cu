@@ -479,6 +479,13 @@ int fw_scene_mesh_leaf_order(const fw_scene* sc, int obj, int* out, int cap) {
         }
     return m.tri_count;
 }
+int fw_scene_bvh_nodes(const fw_scene* sc, float* out, int cap_nodes, int* top_root_code) {
+    if (!sc || !sc->built) return set_error(FW_ERR_STATE, "scene not built (fw_scene_build_host / fw_scene_commit)");
+    int n = (int)(sc->flat.nodes.size() / 8);
+    if (out) memcpy(out, sc->flat.nodes.data(), sizeof(float4) * 8 * (size_t)std::max(0, std::min(n, cap_nodes)));
+    if (top_root_code) *top_root_code = sc->flat.top_root_code;
+    return n;
+}
 int fw_scene_linear_program(const fw_scene* sc, float* out, int cap) {
     if (!sc || !sc->built) return set_error(FW_ERR_STATE, "scene not built (fw_scene_build_host / fw_scene_commit)");
     int n = (int)sc->flat.lin_words.size();

@@ -91,6 +91,14 @@ class NativeScene:
         N.check(N.lib().fw_scene_mesh_leaf_order(self._h, obj, N.ptr(out), n))
         return out
 
+    def bvh_nodes(self):
+        """(nodes (n, 8, 4) float32 — int fields are bit patterns —, top-level root code)."""
+        root = C.c_int()
+        n = N.check(N.lib().fw_scene_bvh_nodes(self._h, None, 0, C.byref(root)))
+        out = np.zeros((max(n, 1), 8, 4), np.float32)
+        N.check(N.lib().fw_scene_bvh_nodes(self._h, N.ptr(out), n, C.byref(root)))
+        return out[:n], root.value
+
     def linear_program(self):
         """The scene's linear-scan program as an (n_words, 4) float32 array (fw_types.h LinItem encoding)."""
         n = N.check(N.lib().fw_scene_linear_program(self._h, None, 0))

@@ -89,6 +89,9 @@ int fw_scene_top_leaf_order(const fw_scene* scene, int* out, int capacity);     
 int fw_scene_object_aabb(const fw_scene* scene, int object, float out_min_max[6]);   /* scene.rs:167-212 */
 int fw_scene_mesh_leaf_order(const fw_scene* scene, int object, int* out, int capacity); /* triangle ids */
 uint64_t fw_scene_device_bytes(const fw_scene* scene);  /* host->device bytes copied by fw_scene_commit */
+/* The flattened 4-wide BVH nodes of all trees (top-level tree first; 32 floats per node, layout in
+ * firework_b200/csrc/fw_types.h) and the top-level root code.  Copies up to `capacity_nodes` nodes, returns the count. */
+int fw_scene_bvh_nodes(const fw_scene* scene, float* out_nodes, int capacity_nodes, int* top_root_code);
 /* The linear-scan program of the scene (SceneInternal::hit, src/scene.rs:137-149, compiled to 16-byte words;
  * encoding in firework_b200/csrc/fw_types.h LinItem).  Copies up to `capacity_words` words (4 floats each) and
  * returns the program's length in words. */

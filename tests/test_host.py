@@ -240,3 +240,66 @@ def test_asset_loaders_report_errors(tmp_path):
     nothdr.write_bytes(b"P6\n1 1\n255\n\0\0\0")
     with pytest.raises(FireworkError, match="not a Radiance"):
         load_hdr(str(nothdr))
+
+
+def _top_tree_leaves(ns):
+    """Walk the flattened top-level tree: {leaf code: (box lo, box hi)} and the boxes of every interior slot with the
+    leaf boxes below it (for the containment check)."""
+    nodes, root = ns.bvh_nodes()
+    codes = nodes[:, 6, :].view(np.int32)
+    leaves, checks = {}, []
+
+    def walk(code):
+        """returns the list of (lo, hi) leaf boxes below `code`"""
+        below = []
+        for k in range(4):
+            c = int(codes[code, k])
+            if c == -2147483648:
+                continue  # empty slot
+            lo, hi = nodes[code, 0:3, k].copy(), nodes[code, 3:6, k].copy()
+            if c >= 0:
+                sub = walk(c)
+                checks.append((lo, hi, sub))
+                below += sub
+            else:
+                assert c not in leaves
+                leaves[c] = (lo, hi)
+                below.append((lo, hi))
+        return below
+
+    if root >= 0:
+        walk(root)
+    return leaves, checks
+
+
+@pytest.mark.parametrize("name", ["random_spheres", "part2_all", "teapot"])
+def test_reclustered_bvh_keeps_the_references_leaves(name):
+    """The SAH interior must sit on exactly the reference's leaves: same leaf codes (item ranges in DFS order), same
+    leaf boxes bit for bit as the tree built with the reference's own interior (FW_BVH_SAH=0, separate process), every
+    item covered once, and every interior slot box must contain all the leaf boxes below it."""
+    import subprocess
+    import sys
+    ns = native_scene(name, commit=False)
+    ns.build_host()
+    leaves, checks = _top_tree_leaves(ns)
+    n_obj = ns.num_objects()
+    ns.close()
+    covered = []
+    for c in leaves:
+        p = ~c
+        covered += list(range(p >> 1, (p >> 1) + (p & 1) + 1))
+    assert sorted(covered) == list(range(n_obj))
+    for lo, hi, sub in checks:
+        for llo, lhi in sub:
+            assert np.all(lo <= llo) and np.all(lhi <= hi)
+    prog = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from test_host import _top_tree_leaves; from conftest import native_scene\n"
+            "ns = native_scene(%r, commit=False); ns.build_host(); l, _ = _top_tree_leaves(ns)\n"
+            "print(json.dumps({str(k): [v[0].tolist(), v[1].tolist()] for k, v in l.items()}))\n"
+            % (REPO, os.path.join(REPO, "tests"), name))
+    out = subprocess.run([sys.executable, "-c", prog], env=dict(os.environ, FW_BVH_SAH="0"), capture_output=True, text=True, check=True).stdout
+    import json
+    ref = json.loads(out.strip().splitlines()[-1])
+    assert set(ref) == {str(k) for k in leaves}
+    for k, (lo, hi) in leaves.items():
+        assert np.array_equal(np.array(ref[str(k)][0], np.float32), lo) and np.array_equal(np.array(ref[str(k)][1], np.float32), hi)
