@@ -513,6 +513,11 @@ int fw_release_cached_memory(void) {
         else destroy_ctx(c);
     }
     g_ctx_cache.swap(keep);
+    {
+        std::lock_guard<std::mutex> lk2(g_staging_mutex);
+        for (HdrStaging* h : g_staging)
+            if (!h->in_use && h->p) { cudaFreeHost(h->p); h->p = nullptr; h->floats = 0; }
+    }
     return FW_OK;
 }
 int fw_set_profiling(fw_scene* sc, int enabled) {
