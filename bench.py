@@ -264,11 +264,16 @@ def main():
 
     # ---- e2e: host YAML text + host texels in, host u8 image out, every step ---------------------------------
     def e2e_step():
+        t_a = time.perf_counter()
         s = NativeScene(text, device=local_rank, assets=assets)      # parse, BVH build, flatten, H2D
+        t_b = time.perf_counter()
         r2 = cfg.renderer(width=width, height=height, samples=spp_total, seed=1)
         if world == 1:
-            rgb, _, _ = s.render(r2.params(), want_sum=False)        # render + D2H into a host buffer
+            rgb, _, st2 = s.render(r2.params(), want_sum=False)      # render + D2H into a host buffer
             d2h = rgb.nbytes
+            if os.environ.get("FW_BENCH_DEBUG"):
+                print(f"[bench] e2e scene {1e3 * (t_b - t_a):.1f} ms, render call {1e3 * (time.perf_counter() - t_b):.1f} ms, "
+                      f"device {st2['ms_device']:.1f} ms", file=sys.stderr)
         else:
             sh = GpuShardRenderer(s, r2, local_rank)
             rgb, _ = render_sharded(sh.render_shard, sh.resolve, spp_total, rank, world)
@@ -283,8 +288,11 @@ def main():
     h2d = d2h = 0
     n_e2e = max(1, min(args.steps, 3))
     for _ in range(n_e2e):
+        t_step = time.perf_counter()
         a, b = e2e_step()
         h2d, d2h = a, max(d2h, b)
+        if os.environ.get("FW_BENCH_DEBUG"):
+            print(f"[bench] e2e step {1e3 * (time.perf_counter() - t_step):.1f} ms", file=sys.stderr)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

@@ -102,6 +102,20 @@ struct RenderCtx {
     unsigned long long* h_rays = nullptr;   // pinned
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // Scene tables live in one device arena that the next scene on this context simply overwrites: committing and
+    // releasing a scene costs no cudaMalloc / cudaFree (each cudaFree is a device-wide synchronisation; 17 of them
+    // per scene made fw_scene_destroy take 200-500 ms inside a process that also runs torch).
+    char* arena = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
+    std::vector<void*> arena_retired;   // outgrown slabs, freed when the scene that may still use them is released
+    // Texture arrays are kept for the next scene that needs the same geometry (the usual case: the same scene again).
+    struct CachedTex {
+        cudaArray_t arr = nullptr;
+        cudaTextureObject_t tex = 0;
+        uint32_t w = 0, h = 0;
+        bool is_float = false, in_use = false;
+    };
+    std::vector<CachedTex> tex_cache;
 };
 static std::mutex g_ctx_mutex;
 static std::vector<RenderCtx*> g_ctx_cache;
@@ -118,9 +132,6 @@ struct fw_scene {
     DeviceScene dscene{};
     LinProgram lin_prog{};     // linear-scan program, passed to the kernels by value (kernel-parameter space)
     bool lin_prog_ok = false;  // the scene's program fits FW_LIN_MAX_WORDS (else: object-loop kernels)
-    std::vector<void*> allocs;
-    std::vector<cudaArray_t> arrays;
-    std::vector<cudaTextureObject_t> texobjs;
     bool mat_present[MAT_NUM_QUEUES] = {false, false, false, false, false, false};
     std::vector<HdrStaging*> hdr_staging;   // per asset: pinned RGBA copy of an HDR map (set_hdr .. commit)
     bool miss_is_zero = false;  // every escaping path contributes exactly 0: the miss kernel is not launched
@@ -129,14 +140,31 @@ struct fw_scene {
     bool profiling = false;
 };
 
+static int arena_alloc(fw_scene* sc, size_t bytes, void** out) {
+    RenderCtx* c = sc->ctx;
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (c->arena_used + bytes > c->arena_cap) {
+        size_t cap = std::max<size_t>((size_t)8 << 20, 2 * (c->arena_used + bytes));
+        char* slab = nullptr;
+        FW_CUDA(cudaMalloc(&slab, cap));
+        // tables already placed for this scene stay valid in the old slab until the scene is released
+        if (c->arena) c->arena_retired.push_back(c->arena);
+        c->arena = slab;
+        c->arena_cap = cap;
+        c->arena_used = 0;
+    }
+    *out = c->arena + c->arena_used;
+    c->arena_used += bytes;
+    return FW_OK;
+}
 template <class T>
 static int upload(fw_scene* sc, const std::vector<T>& host, const T** dev) {
     size_t bytes = std::max<size_t>(host.size() * sizeof(T), 64);
     void* p = nullptr;
-    FW_CUDA(cudaMalloc(&p, bytes));
-    sc->allocs.push_back(p);
-    FW_CUDA(cudaMemset(p, 0, bytes));
-    if (!host.empty()) FW_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    int rc = arena_alloc(sc, bytes, &p);
+    if (rc != FW_OK) return rc;
+    if (host.empty()) FW_CUDA(cudaMemsetAsync(p, 0, bytes, sc->ctx->stream));
+    else FW_CUDA(cudaMemcpyAsync(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, sc->ctx->stream));
     sc->h2d_bytes += host.size() * sizeof(T);
     *dev = reinterpret_cast<const T*>(p);
     return FW_OK;
@@ -153,6 +181,9 @@ static void destroy_ctx(RenderCtx* c) {
     cudaSetDevice(c->device);
     auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     free_path_state(c->ps);
+    if (c->arena) cudaFree(c->arena);
+    for (void* p : c->arena_retired) cudaFree(p);
+    for (auto& t : c->tex_cache) { if (t.tex) cudaDestroyTextureObject(t.tex); if (t.arr) cudaFreeArray(t.arr); }
     fr(c->d_sum); fr(c->d_rgb);
     if (c->h_rays) cudaFreeHost(c->h_rays);
     if (c->d_rays) cudaFree(c->d_rays);
@@ -198,14 +229,20 @@ static void release_device(fw_scene* sc) {
     cudaSetDevice(sc->device);
     if (sc->ctx) {
         cudaStreamSynchronize(sc->ctx->stream);
+        RenderCtx* c = sc->ctx;
+        for (void* p : c->arena_retired) cudaFree(p);
+        c->arena_retired.clear();
+        c->arena_used = 0;                       // the next scene overwrites the tables
+        for (auto& t : c->tex_cache) t.in_use = false;
+        while (c->tex_cache.size() > 8) {        // keep the cache small: drop the oldest idle entries
+            if (c->tex_cache.front().tex) cudaDestroyTextureObject(c->tex_cache.front().tex);
+            if (c->tex_cache.front().arr) cudaFreeArray(c->tex_cache.front().arr);
+            c->tex_cache.erase(c->tex_cache.begin());
+        }
         std::lock_guard<std::mutex> lk(g_ctx_mutex);
-        sc->ctx->in_use = false;  // back to the cache
+        c->in_use = false;  // back to the cache
         sc->ctx = nullptr;
     }
-    for (auto t : sc->texobjs) cudaDestroyTextureObject(t);
-    for (auto a : sc->arrays) cudaFreeArray(a);
-    for (auto p : sc->allocs) cudaFree(p);
-    sc->texobjs.clear(); sc->arrays.clear(); sc->allocs.clear();
     sc->committed = false;
 }
 
@@ -311,27 +348,38 @@ int fw_scene_set_hdr(fw_scene* sc, int i, uint32_t w, uint32_t h, const float* r
 }
 
 static int make_texture(fw_scene* sc, const void* src, uint32_t w, uint32_t h, bool is_float, cudaTextureObject_t* out) {
-    cudaChannelFormatDesc fmt = is_float ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
-    cudaArray_t arr = nullptr;
-    FW_CUDA(cudaMallocArray(&arr, &fmt, w, h));
-    sc->arrays.push_back(arr);
+    RenderCtx* c = sc->ctx;
     size_t row = (size_t)w * (is_float ? 16 : 4);
-    FW_CUDA(cudaMemcpy2DToArray(arr, 0, 0, src, row, row, h, cudaMemcpyHostToDevice));
     sc->h2d_bytes += row * h;
+    for (auto& t : c->tex_cache)
+        if (!t.in_use && t.w == w && t.h == h && t.is_float == is_float) {   // same geometry: refill the array
+            FW_CUDA(cudaMemcpy2DToArrayAsync(t.arr, 0, 0, src, row, row, h, cudaMemcpyHostToDevice, c->stream));
+            t.in_use = true;
+            *out = t.tex;
+            return FW_OK;
+        }
+    cudaChannelFormatDesc fmt = is_float ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
+    RenderCtx::CachedTex t;
+    FW_CUDA(cudaMallocArray(&t.arr, &fmt, w, h));
+    cudaError_t e = cudaMemcpy2DToArrayAsync(t.arr, 0, 0, src, row, row, h, cudaMemcpyHostToDevice, c->stream);
     cudaResourceDesc rd;
     memset(&rd, 0, sizeof(rd));
     rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = arr;
+    rd.res.array.array = t.arr;
     cudaTextureDesc td;
     memset(&td, 0, sizeof(td));
     td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
     td.filterMode = cudaFilterModePoint;  // nearest texel: texture.rs:296-309, hdri_test.rs:72-81
     td.readMode = cudaReadModeElementType;
     td.normalizedCoords = 0;
-    cudaTextureObject_t t = 0;
-    FW_CUDA(cudaCreateTextureObject(&t, &rd, &td, nullptr));
-    sc->texobjs.push_back(t);
-    *out = t;
+    if (e == cudaSuccess) e = cudaCreateTextureObject(&t.tex, &rd, &td, nullptr);
+    if (e != cudaSuccess) {
+        cudaFreeArray(t.arr);
+        return set_error(FW_ERR_CUDA, std::string("texture upload: ") + cudaGetErrorString(e));
+    }
+    t.w = w; t.h = h; t.is_float = is_float; t.in_use = true;
+    c->tex_cache.push_back(t);
+    *out = t.tex;
     return FW_OK;
 }
 
@@ -445,6 +493,8 @@ int fw_scene_commit(fw_scene* sc, int device) {
     if (const char* e = getenv("FW_LINEAR_PROGRAM")) sc->lin_prog_ok = sc->lin_prog_ok && atoi(e) != 0;
     memset(&sc->lin_prog, 0, sizeof(sc->lin_prog));
     if (sc->lin_prog_ok) memcpy(sc->lin_prog.w, F.lin_words.data(), F.lin_words.size() * sizeof(float4));
+    // uploads ran on the context's stream; renders may be issued on another one (fw_render_accumulate_device)
+    FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     sc->committed = true;
     return FW_OK;
 }

@@ -8,7 +8,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cornell_box"
 cfg = CONFIGS[name]; p = cfg.path()
 text = (gzip.open(p, "rt") if p.endswith(".gz") else open(p)).read()
 keep = NativeScene(text, asset_dir=ASSETS)           # like bench: one scene stays alive
-prm = cfg.renderer(samples=cfg.samples, seed=1).params()
+prm = cfg.renderer(samples=int(sys.argv[2]) if len(sys.argv) > 2 else cfg.samples, seed=1).params()
 keep.render(prm, want_sum=False)
 for i in range(5):
     t0 = time.perf_counter()
