@@ -173,6 +173,21 @@ def test_cornell_matches_reference_png():
         assert np.abs(got - np.array(pin["mean_rgb"])).max() < 6.0, (name, got, pin["mean_rgb"])
 
 
+def test_oracle_matches_the_references_suzanne_png():
+    """suzanne.png (examples/suzanne.rs:83-96) is a render of the committed scenes/suzanne.yml with the example's camera:
+    the oracle's render of the same document agrees with it after an 8x8 box filter.  At the 24 spp a CPU test can
+    afford the comparison is noise-limited (~35 dB); the GPU path reaches 51 dB at 512 spp
+    (tests/test_gpu_parity.py::test_render_matches_the_references_committed_png)."""
+    g = np.load(os.path.join(HERE, "golden", "reference_png_lowres.npz"))
+    w, h = (int(v) for v in g["suzanne_size"])
+    sc = oracle_scene("suzanne", fast=True)
+    rgb, _, _ = sc.render(params_for("suzanne", w, h, 24, seed=3))
+    low = rgb[:h // 8 * 8, :w // 8 * 8].astype(np.float64).reshape(h // 8, 8, w // 8, 8, 3).mean((1, 3))
+    d = low - g["suzanne"].astype(np.float64)
+    assert 10.0 * np.log10(255.0 ** 2 / np.mean(d ** 2)) >= 32.0
+    assert np.abs(d).mean() <= 5.0
+
+
 def test_oracle_golden_regression():
     """The oracle's own outputs on fixed inputs (tests/golden/make_oracle_golden.py) — guards against drift."""
     g = np.load(os.path.join(HERE, "golden", "oracle_golden.npz"))
