@@ -10,9 +10,10 @@
 // PARITY: the reference has no tests, no golden vectors, and cannot be compiled here (no Rust toolchain, nightly
 // features, un-vendored crates), so no function of this restatement is pinned by a reference TEST.  What pins it
 // is the reference's committed ARTEFACTS (fixtures + generating scripts under tests/golden/):
-//   * suzanne.png / teapot.png, renders of the committed scenes/*.yml with the examples' cameras: this oracle and
-//     the CUDA path reproduce them end to end (8x8 box means: oracle ~35 dB at 24 spp, noise-limited; GPU 51 dB /
-//     45 dB at 512 / 256 spp) — geometry, orientation, normals, sky, light, gamma;
+//   * suzanne.png / teapot.png / conics.png (renders of the committed scenes/*.yml with the examples' cameras),
+//     cornell_box.png and Earth.png (deterministic example scenes): this oracle and the CUDA path reproduce them end
+//     to end (8x8 box means: oracle ~35 dB at 24 spp, noise-limited; GPU 43-51 dB at 256-1000 spp) — geometry,
+//     orientation, every shape's hit routine, normals, image-texture uv, sky, lights, output transform;
 //   * cornell_box.png patch means (handedness, rotation sign, radiometry of the path loop);
 //   * the Rotor3 values and mesh arrays serialised in scenes/suzanne.yml / teapot.yml (rotor constructors, OBJ ingestion).
 // Everything else (per-function operation order, tie rules, quirks) is a reading of the cited lines, checked by

@@ -1,19 +1,24 @@
 """Generates tests/golden/reference_png_lowres.npz from the renders committed in the reference repository.
 
-Run in the build container only (/root/reference is not on the GPU box).  suzanne.png (960x540, examples/suzanne.rs)
-and teapot.png (1920x1080, examples/teapot.rs) are renders of scenes whose serde dumps are committed next to them
-(scenes/suzanne.yml, scenes/teapot.yml) with cameras fixed in the examples, so — unlike random_spheres.png — they can
-be reproduced.  The fixture holds their 8x8 box-filtered RGB means (noise-suppressed, 1/64 of the pixels); the GPU test
-renders the same scenes at the same resolution and compares box means (tests/test_gpu_parity.py).
+Run in the build container only (/root/reference is not on the GPU box).  These PNGs are renders of scenes that can be
+reproduced exactly — the serde dumps scenes/suzanne.yml, teapot.yml, conics.yml, and the deterministic scene
+constructors of examples/cornell_box.rs, earth.rs — with cameras fixed in the examples (unlike
+random_spheres.png / part2_final.png, whose scenes come from an RNG crate that is not vendored).  The fixture holds
+their 8x8 box-filtered RGB means (noise-suppressed, 1/64 of the pixels); the GPU test renders the same scenes at the
+same resolution and compares box means (tests/test_gpu_parity.py).
 """
 import os
 import numpy as np
 from PIL import Image
 
 REF = "/root/reference"
+# volume.png is left out: it was rendered with a camera / sphere size that the current examples/volume_test.rs no longer
+# has (the sphere fills twice the height it does with the example's camera), so it cannot be reproduced.
+FILES = {"suzanne": "suzanne.png", "teapot": "teapot.png", "cornell_box": "cornell_box.png", "conics": "conics.png",
+         "earth": "Earth.png"}
 out = {}
-for name in ("suzanne", "teapot"):
-    img = np.asarray(Image.open(os.path.join(REF, f"{name}.png")).convert("RGB")).astype(np.float64)
+for name, fn in FILES.items():
+    img = np.asarray(Image.open(os.path.join(REF, fn)).convert("RGB")).astype(np.float64)
     h, w, _ = img.shape
     low = img[:h // 8 * 8, :w // 8 * 8].reshape(h // 8, 8, w // 8, 8, 3).mean((1, 3))
     out[name] = np.round(low, 2).astype(np.float32)

@@ -17,8 +17,11 @@ pytestmark = pytest.mark.gpu
 
 REL = 1e-5  # the tolerance BASELINE.json states for t / normal / scatter
 # agreement with the reference's own committed renders (8x8 box means; measured: see the test's print)
-PNG_PSNR_MIN = {"suzanne": 45.0, "teapot": 40.0}      # measured 51.0 dB / 45.2 dB
-PNG_MEAN_ABS_MAX = {"suzanne": 1.5, "teapot": 2.0}    # measured 0.49 / 0.87 (of 255)
+#                suzanne  teapot  cornell_box  conics  earth
+# measured dB      51.0    45.2      44.2      49.5    43.3
+# mean abs /255    0.49    0.87      1.15      0.51    1.37
+PNG_PSNR_MIN = {"suzanne": 45.0, "teapot": 40.0, "cornell_box": 40.0, "conics": 44.0, "earth": 40.0}
+PNG_MEAN_ABS_MAX = {"suzanne": 1.5, "teapot": 2.0, "cornell_box": 2.5, "conics": 1.5, "earth": 2.5}
 
 
 def _rel(a, b, floor=1e-20):
@@ -347,18 +350,24 @@ def test_cli_checkpoint_resume(tmp_path, scenes):
     assert np.allclose(np.load(ck)["sums"], s, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("name,spp", [("suzanne", 512), ("teapot", 256)])
-def test_render_matches_the_references_committed_png(scenes, name, spp):
-    """The only end-to-end artefacts the reference ships: suzanne.png (examples/suzanne.rs:83-96, 960x540) and teapot.png
-    (examples/teapot.rs:96-109, 1920x1080) are renders of the committed scenes/*.yml with the examples' cameras.  The
-    GPU render of the same document at the same resolution must agree with them after an 8x8 box filter (their sample
-    count and RNG differ, so the comparison is noise-limited): geometry, mesh orientation, flat vs interpolated normals,
-    the sky, the light and gamma all show up here.  Fixture: tests/golden/reference_png_lowres.npz."""
+@pytest.mark.parametrize("name,spp,gamma", [("suzanne", 512, 2.2), ("teapot", 256, 2.2), ("cornell_box", 1000, 2.0),
+                                            ("conics", 256, 2.2), ("earth", 256, 2.2)])
+def test_render_matches_the_references_committed_png(scenes, name, spp, gamma):
+    """The only end-to-end artefacts the reference ships: renders of scenes that can be reproduced exactly —
+    suzanne.png (examples/suzanne.rs:83-96, 960x540), teapot.png (examples/teapot.rs:96-109, 1920x1080) and conics.png
+    (examples/conics.rs:85-93) from the committed scenes/*.yml, cornell_box.png (examples/cornell_box.rs, 300x300;
+    rendered by an older revision whose output gamma was 2.0) and Earth.png (examples/earth.rs, 800x800).  The GPU render
+    of the same scene at the same resolution must agree with them after an 8x8 box filter (their sample count and RNG
+    differ, so the comparison is noise-limited): geometry, orientation, every shape's hit routine, flat vs interpolated
+    normals, image-texture uv, the sky, the lights and the output transform all show up here.
+    Fixture: tests/golden/reference_png_lowres.npz (generator beside it)."""
     import os
     ns, _ = scenes(name)
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_png_lowres.npz"))
     w, h = (int(v) for v in g[name + "_size"])
-    rgb, _, _ = ns.render(params_for(name, w, h, spp, seed=5), want_sum=False)
+    p = params_for(name, w, h, spp, seed=5)
+    p.gamma = gamma
+    rgb, _, _ = ns.render(p, want_sum=False)
     low = rgb[:h // 8 * 8, :w // 8 * 8].astype(np.float64).reshape(h // 8, 8, w // 8, 8, 3).mean((1, 3))
     d = low - g[name].astype(np.float64)
     psnr = 10.0 * np.log10(255.0 ** 2 / np.mean(d ** 2))
