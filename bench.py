@@ -233,12 +233,14 @@ def main():
         img, _ = render_sharded(render_shard, shard.resolve, spp_total, rank, world)
         return img
 
+    # nvidia-smi needs ~0.1-0.3 s before its first sample: start it before the warm-up so that even a 150 ms timed
+    # region is covered; only samples inside the timed window are used
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(warmup):
         step()
     barrier()
     for k in totals:
         totals[k] = 0
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.time()
     for e0, e1 in evs:
