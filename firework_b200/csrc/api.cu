@@ -850,6 +850,7 @@ static int render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStrea
             b.pix0 = (uint32_t)pix0; b.npix = (uint32_t)np;
             b.s0 = p->sample_begin + s; b.ns = std::min(chunk, p->sample_count - s);
             b.width = p->width; b.height = p->height;
+            b.npix_magic = np <= 1 ? 0xffffffffu : (uint32_t)((((uint64_t)1 << 32) + np - 1) / np);
             if ((rc = run_batch(sc, cam, b, seed, p->use_bvh != 0, d_sum, st, tot, ev_next)) != FW_OK) return rc;
         }
     }

@@ -75,11 +75,18 @@ FW_DEV uint32_t* counter_row(const PathState& ps, uint32_t row, int queue) {
 struct Batch {
     uint32_t pix0, npix, s0, ns;
     uint32_t width, height;
+    uint32_t npix_magic;   // ceil(2^32 / npix) (0xffffffff for npix == 1): p / npix without the emulated 32-bit division
 };
 
+// pixel = pix0 + p % npix, sample = s0 + p / npix.  q = umulhi(p, ceil(2^32 / npix)) is floor(p / npix) or one more
+// (one less for npix == 1); one correction step makes it exact for every 32-bit p.
 FW_DEV void batch_path(const Batch& b, uint32_t p, uint32_t& pixel, uint32_t& sample) {
-    pixel = b.pix0 + p % b.npix;
-    sample = b.s0 + p / b.npix;
+    uint32_t q = __umulhi(p, b.npix_magic);
+    int r = (int)(p - q * b.npix);
+    if (r < 0) { q -= 1u; r += (int)b.npix; }
+    else if (r >= (int)b.npix) { q += 1u; r -= (int)b.npix; }
+    pixel = b.pix0 + (uint32_t)r;
+    sample = b.s0 + q;
 }
 
 // render.rs:173-180 + camera.rs:109-116 + util.rs:31-33
