@@ -14,8 +14,8 @@
 #include <vector>
 
 #include "../../include/firework_b200.h"
+#include "launch.h"
 #include "scene_host.h"
-#include "wavefront.cuh"
 
 using namespace fw;
 
@@ -128,7 +128,7 @@ struct fw_scene {
     bool committed = false;  // uploaded to the device
     int device = 0;
     int sm_count = 148;
-    int two_pass = 1;        // two-pass extend for BVH scenes with top-level meshes (FW_TWO_PASS)
+    ExtendPlan plan;         // which extend kernel serves this scene (filled at commit)
     DeviceScene dscene{};
     LinProgram lin_prog{};     // linear-scan program, passed to the kernels by value (kernel-parameter space)
     bool lin_prog_ok = false;  // the scene's program fits FW_LIN_MAX_WORDS (else: object-loop kernels)
@@ -493,6 +493,8 @@ int fw_scene_commit(fw_scene* sc, int device) {
     if (const char* e = getenv("FW_LINEAR_PROGRAM")) sc->lin_prog_ok = sc->lin_prog_ok && atoi(e) != 0;
     memset(&sc->lin_prog, 0, sizeof(sc->lin_prog));
     if (sc->lin_prog_ok) memcpy(sc->lin_prog.w, F.lin_words.data(), F.lin_words.size() * sizeof(float4));
+    sc->plan.has_mesh = F.has_mesh; sc->plan.has_top_mesh = F.has_top_mesh; sc->plan.has_medium_mesh = F.has_medium_mesh;
+    sc->plan.lin_prog_ok = sc->lin_prog_ok; sc->plan.lin_generic = F.lin_generic; sc->plan.lin_rect_tests = F.lin_rect_tests;
     // uploads ran on the context's stream; renders may be issued on another one (fw_render_accumulate_device)
     FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     sc->committed = true;
@@ -659,6 +661,73 @@ static inline unsigned grid_for(size_t n, unsigned threads, unsigned max_blocks)
     return (unsigned)std::max<size_t>(1, std::min<size_t>(g, max_blocks));
 }
 
+// FW_DEBUG_STEPS=1: per-path box-test counts of one bounce, worst path printed to stderr (FW_DEBUG_DUMP: per-bounce dump).
+static int debug_extend(fw_scene* sc, const Batch& b, uint2 seed, uint32_t bounce, cudaStream_t st) {
+    PathState& ps = sc->ctx->ps;
+    const DeviceScene& S = sc->dscene;
+    const uint32_t N = b.npix * b.ns;
+    // debug: per-path box-test counts, worst path of every bounce printed to stderr
+    static uint32_t* d_steps = nullptr;
+    static size_t d_steps_cap = 0;
+    if (d_steps_cap < ps.cap) {
+        if (d_steps) cudaFree(d_steps);
+        FW_CUDA(cudaMalloc(&d_steps, (size_t)ps.cap * 4));
+        d_steps_cap = ps.cap;
+    }
+    FW_CUDA(cudaMemsetAsync(d_steps, 0xff, (size_t)ps.cap * 4, st));   // 0xffffffff = path not traced this bounce
+    launch_extend_debug(S, ps, b, seed, bounce, d_steps, st);
+    FW_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint32_t> hs(N);
+    FW_CUDA(cudaMemcpy(hs.data(), d_steps, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    size_t worst = 0;
+    unsigned long long sum = 0;
+    bool any = false;
+    for (size_t i = 0; i < N; ++i) {
+        if (hs[i] == 0xffffffffu) continue;
+        sum += hs[i];
+        if (!any || hs[i] > hs[worst]) { worst = i; any = true; }
+    }
+    // the segments' extend-queue records of this bounce: (o, path), (d, -)
+    std::vector<float4> qo, qd;
+    {
+        std::vector<uint32_t> cnts(ps.nseg);
+        FW_CUDA(cudaMemcpy(cnts.data(), ps.counters + ((size_t)bounce * FW_NUM_QUEUES + FW_Q_EXTEND) * ps.nseg,
+                           (size_t)ps.nseg * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t seg = 0; seg < ps.nseg; ++seg) {
+            if (!cnts[seg]) continue;
+            size_t at = qo.size();
+            qo.resize(at + cnts[seg]); qd.resize(at + cnts[seg]);
+            FW_CUDA(cudaMemcpy(qo.data() + at, ps.xo[bounce & 1] + (size_t)seg * ps.seg_cap, (size_t)cnts[seg] * 16, cudaMemcpyDeviceToHost));
+            FW_CUDA(cudaMemcpy(qd.data() + at, ps.xd[bounce & 1] + (size_t)seg * ps.seg_cap, (size_t)cnts[seg] * 16, cudaMemcpyDeviceToHost));
+        }
+    }
+    float4 ro = make_float4(0, 0, 0, 0), rd = ro;
+    for (size_t i = 0; i < qo.size(); ++i) {
+        uint32_t pth;
+        memcpy(&pth, &qo[i].w, 4);
+        if (pth == worst) { ro = qo[i]; rd = qd[i]; }
+    }
+    if (const char* dump = getenv("FW_DEBUG_DUMP")) {
+        // per-bounce dump for offline coherence analysis: queue order, per-path box tests, rays
+        uint32_t cnt = (uint32_t)qo.size();
+        std::string fn = std::string(dump) + "_b" + std::to_string(bounce) + ".bin";
+        FILE* f = fopen(fn.c_str(), "wb");
+        if (f) {
+            fwrite(&cnt, 4, 1, f);
+            for (uint32_t i = 0; i < cnt; ++i) {
+                uint32_t pth;
+                memcpy(&pth, &qo[i].w, 4);
+                float rec[8] = {qo[i].x, qo[i].y, qo[i].z, qd[i].x, qd[i].y, qd[i].z, (float)hs[pth], (float)pth};
+                fwrite(rec, 4, 8, f);
+            }
+            fclose(f);
+        }
+    }
+    fprintf(stderr, "[fw debug] bounce %u: box tests total %llu, worst path %zu (pixel %zu sample %zu): %u tests, o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g)\n",
+            bounce, sum, worst, (size_t)b.pix0 + worst % b.npix, (size_t)b.s0 + worst / b.npix, any ? hs[worst] : 0u, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
+    return FW_OK;
+}
+
 // One batch: raygen, up to FW_MAX_DEPTH+1 extend/shade rounds, accumulate into d_sum.
 static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 seed, bool use_bvh, float* d_sum,
                      cudaStream_t st, RunTotals& tot, size_t& ev_next) {
@@ -669,8 +738,7 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
     const size_t counter_bytes = sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * (size_t)ps.nseg;
     FW_CUDA(cudaMemsetAsync(ps.counters, 0, counter_bytes, st));
     unsigned sm = (unsigned)sc->sm_count;
-    const unsigned G = ps.nseg;   // one block per segment, in every queue-driven kernel
-    raygen_kernel<<<G, FW_BLOCK, 0, st>>>(cam, b, seed, ps);
+    launch_raygen(cam, b, seed, ps, st);
     tot.launches++;
     for (uint32_t bounce = 0; bounce <= (uint32_t)FW_MAX_DEPTH; ++bounce) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -680,136 +748,36 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
             FW_CUDA(cudaEventRecord(e0, st));
         }
         if (use_bvh && getenv("FW_DEBUG_STEPS")) {
-            // debug: per-path box-test counts, worst path of every bounce printed to stderr
-            static uint32_t* d_steps = nullptr;
-            static size_t d_steps_cap = 0;
-            if (d_steps_cap < ps.cap) {
-                if (d_steps) cudaFree(d_steps);
-                FW_CUDA(cudaMalloc(&d_steps, (size_t)ps.cap * 4));
-                d_steps_cap = ps.cap;
-            }
-            FW_CUDA(cudaMemsetAsync(d_steps, 0xff, (size_t)ps.cap * 4, st));   // 0xffffffff = path not traced this bounce
-            extend_bvh_debug_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, d_steps);
-            FW_CUDA(cudaStreamSynchronize(st));
-            std::vector<uint32_t> hs(N);
-            FW_CUDA(cudaMemcpy(hs.data(), d_steps, (size_t)N * 4, cudaMemcpyDeviceToHost));
-            size_t worst = 0;
-            unsigned long long sum = 0;
-            bool any = false;
-            for (size_t i = 0; i < N; ++i) {
-                if (hs[i] == 0xffffffffu) continue;
-                sum += hs[i];
-                if (!any || hs[i] > hs[worst]) { worst = i; any = true; }
-            }
-            // the segments' extend-queue records of this bounce: (o, path), (d, -)
-            std::vector<float4> qo, qd;
-            {
-                std::vector<uint32_t> cnts(ps.nseg);
-                FW_CUDA(cudaMemcpy(cnts.data(), ps.counters + ((size_t)bounce * FW_NUM_QUEUES + FW_Q_EXTEND) * ps.nseg,
-                                   (size_t)ps.nseg * 4, cudaMemcpyDeviceToHost));
-                for (uint32_t seg = 0; seg < ps.nseg; ++seg) {
-                    if (!cnts[seg]) continue;
-                    size_t at = qo.size();
-                    qo.resize(at + cnts[seg]); qd.resize(at + cnts[seg]);
-                    FW_CUDA(cudaMemcpy(qo.data() + at, ps.xo[bounce & 1] + (size_t)seg * ps.seg_cap, (size_t)cnts[seg] * 16, cudaMemcpyDeviceToHost));
-                    FW_CUDA(cudaMemcpy(qd.data() + at, ps.xd[bounce & 1] + (size_t)seg * ps.seg_cap, (size_t)cnts[seg] * 16, cudaMemcpyDeviceToHost));
-                }
-            }
-            float4 ro = make_float4(0, 0, 0, 0), rd = ro;
-            for (size_t i = 0; i < qo.size(); ++i) {
-                uint32_t pth;
-                memcpy(&pth, &qo[i].w, 4);
-                if (pth == worst) { ro = qo[i]; rd = qd[i]; }
-            }
-            if (const char* dump = getenv("FW_DEBUG_DUMP")) {
-                // per-bounce dump for offline coherence analysis: queue order, per-path box tests, rays
-                uint32_t cnt = (uint32_t)qo.size();
-                std::string fn = std::string(dump) + "_b" + std::to_string(bounce) + ".bin";
-                FILE* f = fopen(fn.c_str(), "wb");
-                if (f) {
-                    fwrite(&cnt, 4, 1, f);
-                    for (uint32_t i = 0; i < cnt; ++i) {
-                        uint32_t pth;
-                        memcpy(&pth, &qo[i].w, 4);
-                        float rec[8] = {qo[i].x, qo[i].y, qo[i].z, qd[i].x, qd[i].y, qd[i].z, (float)hs[pth], (float)pth};
-                        fwrite(rec, 4, 8, f);
-                    }
-                    fclose(f);
-                }
-            }
-            fprintf(stderr, "[fw debug] bounce %u: box tests total %llu, worst path %zu (pixel %zu sample %zu): %u tests, o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g)\n",
-                    bounce, sum, worst, (size_t)b.pix0 + worst % b.npix, (size_t)b.s0 + worst / b.npix, any ? hs[worst] : 0u, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
-        } else if (use_bvh && sc->flat.has_top_mesh && sc->two_pass) {
-            if (sc->flat.has_medium_mesh) {
-                extend_pass1_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-                extend_pass2_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-            } else {
-                extend_pass1_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-                extend_pass2_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-            }
+            int rc = debug_extend(sc, b, seed, bounce, st);
+            if (rc != FW_OK) return rc;
             tot.launches++;
-        } else if (use_bvh) {
-            if (sc->flat.has_medium_mesh)
-                extend_bvh_simple_kernel<true, true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-            else if (sc->flat.has_mesh)
-                extend_bvh_simple_kernel<false, true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-            else
-                extend_bvh_simple_kernel<false, false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-        } else if (sc->lin_prog_ok) {
-            const LinProgram& P = sc->lin_prog;
-            if (sc->flat.lin_generic) {
-                if (sc->flat.has_mesh)
-                    extend_linear_prog_kernel<true, true, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
-                else
-                    extend_linear_prog_kernel<true, false, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
-            } else if (sc->flat.lin_rect_tests >= 8) {   // rectangle-heavy: shared-reciprocal division (SHDIV)
-                // coherent primary rays: whole warps skip Rect3d boxes they do not enter (PRETEST)
-                if (bounce == 0) extend_linear_prog_kernel<false, false, true, true><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
-                else extend_linear_prog_kernel<false, false, false, true><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
-            } else {
-                extend_linear_prog_kernel<false, false, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
-            }
-        } else if (sc->flat.has_mesh) {
-            extend_linear_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
         } else {
-            extend_linear_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+            tot.launches += launch_extend(sc->plan, use_bvh, sc->lin_prog, S, ps, b, seed, bounce, st);
         }
         if (sc->profiling) {
             FW_CUDA(cudaEventRecord(e1, st));
             tot.extend_events.emplace_back(e0, e1);
         }
-        tot.launches++;
         tot.extend_launches++;
         if (!sc->miss_is_zero) {
-            miss_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, bounce);
+            launch_miss(S, ps, bounce, st);
             tot.launches++;
         }
         if (sc->mat_present[MAT_EMISSIVE]) {
-            shade_emissive_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, bounce);
+            launch_shade_emissive(S, ps, bounce, st);
             tot.launches++;
         }
         if (bounce < (uint32_t)FW_MAX_DEPTH) {
-            if (sc->mat_present[MAT_LAMBERTIAN]) {
-                shade_scatter_kernel<MAT_LAMBERTIAN><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-                tot.launches++;
-            }
-            if (sc->mat_present[MAT_METAL]) {
-                shade_scatter_kernel<MAT_METAL><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-                tot.launches++;
-            }
-            if (sc->mat_present[MAT_DIELECTRIC]) {
-                shade_scatter_kernel<MAT_DIELECTRIC><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-                tot.launches++;
-            }
-            if (sc->mat_present[MAT_ISOTROPIC]) {
-                shade_scatter_kernel<MAT_ISOTROPIC><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
-                tot.launches++;
-            }
+            for (int mat : {MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_ISOTROPIC})
+                if (sc->mat_present[mat]) {
+                    launch_shade_scatter(mat, S, ps, b, seed, bounce, st);
+                    tot.launches++;
+                }
         }
     }
-    accumulate_kernel<<<grid_for(b.npix, 256, sm * 8), 256, 0, st>>>(d_sum, ps, b);
+    launch_accumulate(d_sum, ps, b, grid_for(b.npix, 256, sm * 8), st);
     tot.launches++;
-    tally_kernel<<<1, 256, 0, st>>>(ps, sc->ctx->d_rays);
+    launch_tally(ps, sc->ctx->d_rays, st);
     tot.launches++;
     FW_CUDA(cudaGetLastError());
     return FW_OK;
@@ -831,7 +799,7 @@ static int render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStrea
     // from 4 Mi to 32 Mi paths); ~280 B of state per path -> 9 GB, small next to 180 GB of HBM.
     size_t cap = sc->batch_paths ? sc->batch_paths : ((size_t)1 << 25);
     if (const char* e = getenv("FW_BATCH_PATHS")) cap = std::max<size_t>(1024, strtoull(e, nullptr, 10));
-    if (const char* e = getenv("FW_TWO_PASS")) sc->two_pass = atoi(e);
+    if (const char* e = getenv("FW_TWO_PASS")) sc->plan.two_pass = atoi(e) != 0;
     cap = std::min<size_t>(cap, npix * std::max<uint32_t>(p->sample_count, 1));
     cap = std::max<size_t>(cap, 32);
     int rc;
@@ -892,7 +860,7 @@ int fw_resolve_device(fw_scene* sc, const float* d_sum, uint32_t npix, uint32_t 
     if (!sc->committed) return set_error(FW_ERR_STATE, "scene not committed");
     FW_CUDA(cudaSetDevice(sc->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : sc->ctx->stream;
-    resolve_kernel<<<grid_for(npix, 256, sc->sm_count * 8), 256, 0, st>>>(d_sum, npix, (float)samples, gamma, d_rgb);
+    launch_resolve(d_sum, npix, (float)samples, gamma, d_rgb, grid_for(npix, 256, sc->sm_count * 8), st);
     FW_CUDA(cudaGetLastError());
     return FW_OK;
 }
@@ -915,8 +883,7 @@ int fw_render(fw_scene* sc, const fw_params* p, uint8_t* rgb_out, float* sum_out
     int rc = render_into(sc, p, sc->ctx->d_sum, sc->ctx->stream, stats);
     if (rc != FW_OK) return rc;
     if (rgb_out) {
-        resolve_kernel<<<grid_for(npix, 256, sc->sm_count * 8), 256, 0, sc->ctx->stream>>>(sc->ctx->d_sum, (uint32_t)npix,
-                                                                                     (float)p->samples, p->gamma, sc->ctx->d_rgb);
+        launch_resolve(sc->ctx->d_sum, (uint32_t)npix, (float)p->samples, p->gamma, sc->ctx->d_rgb, grid_for(npix, 256, sc->sm_count * 8), sc->ctx->stream);
         FW_CUDA(cudaGetLastError());
         if (stats) stats->launches++;
         FW_CUDA(cudaMemcpyAsync(rgb_out, sc->ctx->d_rgb, npix * 3, cudaMemcpyDeviceToHost, sc->ctx->stream));
@@ -939,9 +906,8 @@ int fw_primary_rays(fw_scene* sc, const fw_params* p, uint32_t sample, uint32_t 
     CameraRec cam = make_camera(hp);
     DevBuf o, d;
     TRY(o.alloc((size_t)n * 12)); TRY(d.alloc((size_t)n * 12));
-    primary_rays_probe<<<grid_for(n, 256, 4096), 256, 0, sc->ctx->stream>>>(cam, p->width, p->height, sample,
-                                                                       make_uint2((uint32_t)p->seed, (uint32_t)(p->seed >> 32)),
-                                                                       pix_begin, n, o.as<float>(), d.as<float>());
+    launch_primary_rays_probe(cam, p->width, p->height, sample, make_uint2((uint32_t)p->seed, (uint32_t)(p->seed >> 32)), pix_begin, n,
+                              o.as<float>(), d.as<float>(), grid_for(n, 256, 4096), sc->ctx->stream);
     FW_CUDA(cudaGetLastError());
     FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     TRY(o.get(origins, (size_t)n * 12)); TRY(d.get(dirs, (size_t)n * 12));
@@ -967,22 +933,9 @@ int fw_first_hit(fw_scene* sc, int use_bvh, uint64_t seed, uint32_t n, const flo
                     oUv.as<float>(), oC.as<unsigned long long>()};
     uint2 sd = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     unsigned g = grid_for(n, 128, 8192);
-    if (use_bvh)
-        first_hit_probe<true><<<g, 128, 0, sc->ctx->stream>>>(sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
-                                                         pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,
-                                                         bounce ? dB.as<uint32_t>() : nullptr, out);
-    else if (sc->lin_prog_ok && sc->flat.lin_generic)
-        first_hit_prog_probe<true><<<g, 128, 0, sc->ctx->stream>>>(sc->lin_prog, sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
-                                                              pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,
-                                                              bounce ? dB.as<uint32_t>() : nullptr, out);
-    else if (sc->lin_prog_ok)
-        first_hit_prog_probe<false><<<g, 128, 0, sc->ctx->stream>>>(sc->lin_prog, sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
-                                                               pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,
-                                                               bounce ? dB.as<uint32_t>() : nullptr, out);
-    else
-        first_hit_probe<false><<<g, 128, 0, sc->ctx->stream>>>(sc->dscene, sd, n, dO.as<float>(), dD.as<float>(),
-                                                          pixel ? dP.as<uint32_t>() : nullptr, sample ? dS.as<uint32_t>() : nullptr,
-                                                          bounce ? dB.as<uint32_t>() : nullptr, out);
+    int mode = use_bvh ? 1 : (sc->lin_prog_ok ? (sc->flat.lin_generic ? 2 : 3) : 0);
+    launch_first_hit_probe(mode, sc->lin_prog, sc->dscene, sd, n, dO.as<float>(), dD.as<float>(), pixel ? dP.as<uint32_t>() : nullptr,
+                           sample ? dS.as<uint32_t>() : nullptr, bounce ? dB.as<uint32_t>() : nullptr, out, g, sc->ctx->stream);
     FW_CUDA(cudaGetLastError());
     FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     TRY(oObj.get(obj, (size_t)n * 4)); TRY(oPrim.get(prim, (size_t)n * 4)); TRY(oMat.get(material, (size_t)n * 4));
@@ -1012,7 +965,7 @@ int fw_scatter_step(fw_scene* sc, uint32_t n, const int32_t* material, const flo
     ScatterProbeIO io{m.as<int>(), ro.as<float>(), rd.as<float>(), ht.as<float>(), hp.as<float>(), hn.as<float>(),
                       hu.as<float>(), un.as<float>(), nu, e.as<float>(), s.as<int>(), a.as<float>(), oo.as<float>(),
                       od.as<float>(), c.as<int>()};
-    scatter_step_probe<<<grid_for(n, 128, 4096), 128, 0, sc->ctx->stream>>>(sc->dscene, n, io);
+    launch_scatter_step_probe(sc->dscene, n, io, grid_for(n, 128, 4096), sc->ctx->stream);
     FW_CUDA(cudaGetLastError());
     FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     TRY(e.get(emit, (size_t)n * 12)); TRY(s.get(scattered, (size_t)n * 4)); TRY(a.get(atten, (size_t)n * 12));
@@ -1026,7 +979,7 @@ int fw_env_sample(fw_scene* sc, uint32_t n, const float* dirs, float* out) {
     FW_CUDA(cudaSetDevice(sc->device));
     DevBuf d, o;
     TRY(d.put(dirs, (size_t)n * 12)); TRY(o.alloc((size_t)n * 12));
-    env_sample_probe<<<grid_for(n, 256, 4096), 256, 0, sc->ctx->stream>>>(sc->dscene, n, d.as<float>(), o.as<float>());
+    launch_env_sample_probe(sc->dscene, n, d.as<float>(), o.as<float>(), grid_for(n, 256, 4096), sc->ctx->stream);
     FW_CUDA(cudaGetLastError());
     FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     return o.get(out, (size_t)n * 12);
@@ -1038,7 +991,7 @@ int fw_texture_sample(fw_scene* sc, int texture, uint32_t n, const float* uv, co
     FW_CUDA(cudaSetDevice(sc->device));
     DevBuf u, p, o;
     TRY(u.put(uv, (size_t)n * 8)); TRY(p.put(point, (size_t)n * 12)); TRY(o.alloc((size_t)n * 12));
-    texture_sample_probe<<<grid_for(n, 256, 4096), 256, 0, sc->ctx->stream>>>(sc->dscene, texture, n, u.as<float>(), p.as<float>(), o.as<float>());
+    launch_texture_sample_probe(sc->dscene, texture, n, u.as<float>(), p.as<float>(), o.as<float>(), grid_for(n, 256, 4096), sc->ctx->stream);
     FW_CUDA(cudaGetLastError());
     FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     return o.get(out, (size_t)n * 12);
@@ -1053,7 +1006,7 @@ int fw_selftest_shared_division(int device, uint64_t n_pairs, uint64_t seed, uin
     DevBuf v;
     TRY(v.alloc(16));
     FW_CUDA(cudaMemset(v.p, 0, 16));
-    shared_division_probe<<<148 * 8, 256>>>(n_pairs, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), v.as<unsigned long long>());
+    launch_shared_division_probe(n_pairs, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), v.as<unsigned long long>());
     FW_CUDA(cudaGetLastError());
     FW_CUDA(cudaDeviceSynchronize());
     return v.get(violations, 16);
@@ -1061,26 +1014,6 @@ int fw_selftest_shared_division(int device, uint64_t n_pairs, uint64_t seed, uin
 
 // ---- roofline denominators ------------------------------------------------------------------------------
 }  // extern "C"
-
-__global__ void fp32_peak_kernel(float* out, int iters) {
-    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
-    const float m = 1.000001f, c = 1e-7f;
-    for (int i = 0; i < iters; ++i) {
-        a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
-        a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
-    }
-    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 123.456f) out[0] = a0;
-}
-__global__ void l2_read_kernel(const float4* __restrict__ buf, size_t n_vec, int reps, float* out) {
-    float acc = 0.f;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (int r = 0; r < reps; ++r)
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-            float4 v = __ldcg(&buf[i]);  // cache-global: served by L2, bypasses L1
-            acc += v.x + v.y + v.z + v.w;
-        }
-    if (acc == 123.456f) out[0] = acc;
-}
 
 extern "C" int fw_measure_peaks(int device, double* fp32_tflops, double* l2_gbs, int* sm_count, int* sm_clock_khz) {
     FW_CUDA(cudaSetDevice(device));
@@ -1099,7 +1032,7 @@ extern "C" int fw_measure_peaks(int device, double* fp32_tflops, double* l2_gbs,
     double best = 0;
     for (int rep = 0; rep < 4; ++rep) {
         FW_CUDA(cudaEventRecord(e0));
-        fp32_peak_kernel<<<blocks, threads>>>(out, iters);
+        launch_fp32_peak(out, iters, blocks, threads);
         FW_CUDA(cudaEventRecord(e1));
         FW_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
@@ -1116,7 +1049,7 @@ extern "C" int fw_measure_peaks(int device, double* fp32_tflops, double* l2_gbs,
     int reps = 20;
     for (int rep = 0; rep < 4; ++rep) {
         FW_CUDA(cudaEventRecord(e0));
-        l2_read_kernel<<<prop.multiProcessorCount * 8, 512>>>(buf, bytes / 16, reps, out);
+        launch_l2_read(buf, bytes / 16, reps, out, prop.multiProcessorCount * 8, 512);
         FW_CUDA(cudaEventRecord(e1));
         FW_CUDA(cudaEventSynchronize(e1));
         float ms = 0;

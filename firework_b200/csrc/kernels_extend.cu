@@ -1,0 +1,165 @@
+// Extend kernels: closest hit for every queued ray (render.rs:19 -> bvh.rs:115-151 / scene.rs:137-149).
+#include "launch.h"
+#include "wavefront.cuh"
+
+namespace fw {
+
+// Debug twin of the BVH extend: also records the number of box tests each path needed (FW_DEBUG_STEPS=1).
+__global__ void __launch_bounds__(FW_BLOCK) extend_bvh_debug_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce,
+                                                                    uint32_t* steps) {
+    FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
+        if (valid) {
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            Counters cnt{0, 0};
+            trace_unified<true, true>(S, o, d, key, w, &cnt);
+            steps[path] = (uint32_t)cnt.node_tests;
+        }
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
+}
+
+// Two-pass extend for BVH scenes with TriangleMesh objects (see UnifiedWalker PHASE).  Pass 1 settles every ray
+// against the non-mesh objects and the mesh root boxes; rays that must enter a mesh are compacted into the mesh
+// queue (with the pass-1 winner and its rank) and finished by pass 2, where every lane of a warp is doing real
+// mesh traversal.
+template <bool NESTED>
+__global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass1_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
+                                                                                uint32_t bounce) {
+    FW_EXTEND_PROLOGUE(FW_NUM_QUEUES)
+        if (valid) {
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            UnifiedWalker<false, NESTED, true, 1> wk;
+            int stack_code[FW_STACK];
+            float stack_te[FW_STACK];
+            if (wk.init(S, o, d, stack_code, stack_te, nullptr)) {
+                while (wk.step(S, key, nullptr)) {
+                }
+            }
+            w = wk.w;
+            if (wk.pending) mine = FW_Q_MESH;   // queue 6 is never selected (its counter slot belongs to the shade kernels)
+        }
+    FW_EXTEND_EPILOGUE(FW_NUM_QUEUES)
+}
+template <bool NESTED>
+__global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass2_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
+                                                                                uint32_t bounce) {
+    __shared__ uint32_t s_fill[FW_NUM_QUEUES];
+    const uint32_t in_count = counter_row(ps, bounce, FW_Q_MESH)[blockIdx.x];
+    if (in_count == 0) return;  // block-uniform
+    seg_open<MAT_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), blockIdx.x);   // continues pass 1's material queues
+    for (uint32_t e0 = 0; e0 < in_count; e0 += FW_BLOCK) {
+        const bool valid = e0 + threadIdx.x < in_count;
+        int mine = -1, material = -1;
+        HitIn h;
+        h.path = 0; h.o = h.d = f3(0.0f, 0.0f, 0.0f);
+        h.w.found = false; h.w.t = 0.0f; h.w.obj = -1; h.w.rank = -1; h.w.h.t = 0.0f; h.w.h.prim = 0;
+        h.w.h.b0 = h.w.h.b1 = h.w.h.b2 = 0.0f;
+        if (valid) {
+            h = get_hit<FW_Q_MESH>(ps, blockIdx.x * ps.seg_cap + e0 + threadIdx.x);
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, h.path, key.pixel, key.sample);
+            UnifiedWalker<false, NESTED, true, 2> wk;
+            wk.w = h.w;   // the pass-1 winner (a non-mesh object) and its rank
+            wk.w.h.b0 = wk.w.h.b1 = wk.w.h.b2 = 0.0f;
+            int stack_code[FW_STACK];
+            float stack_te[FW_STACK];
+            if (wk.init(S, h.o, h.d, stack_code, stack_te, nullptr)) {
+                while (wk.step(S, key, nullptr)) {
+                }
+            }
+            h.w = wk.w;
+            mine = classify_winner(S, h.w, material);
+        }
+        enqueue_hit<MAT_NUM_QUEUES>(ps, s_fill, blockIdx.x * ps.seg_cap, mine, h.o, h.d, h.path, h.w, material);
+    }
+    seg_close<MAT_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), blockIdx.x);
+}
+
+template <bool NESTED, bool MESHES>
+__global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
+                                                                                     uint32_t bounce) {
+    FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
+        if (valid) {
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            trace_unified<false, NESTED, MESHES>(S, o, d, key, w, nullptr);
+        }
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
+}
+
+// Linear-scan scenes (Renderer.use_bvh == false, scene.rs:137-149): every ray tests every object in scene
+// order, so there is no traversal-length divergence to balance.
+// NESTED: the scene contains a TriangleMesh (its own BVH is walked inside the object test).
+// This object-loop form serves scenes whose LinProgram does not fit kernel-parameter space.
+template <bool NESTED>
+__global__ void __launch_bounds__(FW_BLOCK) extend_linear_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce) {
+    FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
+        if (valid) {
+            RngKey key{seed, 0u, 0u, bounce};
+            batch_path(b, path, key.pixel, key.sample);
+            trace_linear_scan<false, NESTED>(S, o, d, key, w, nullptr);
+        }
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
+}
+
+// The same query driven by the scene's LinProgram in kernel-parameter space (intersect.cuh trace_linear_prog):
+// no per-lane loads of scene records, uniform item dispatch.  Every lane of a warp runs the program (lanes past
+// the end of the segment trace a dummy ray and drop the result) so that the PRETEST vote sees the whole warp.
+template <bool GENERIC, bool NESTED, bool PRETEST, bool SHDIV>
+__global__ void __launch_bounds__(FW_BLOCK) extend_linear_prog_kernel(const __grid_constant__ LinProgram P, DeviceScene S, PathState ps,
+                                                                      Batch b, uint2 seed, uint32_t bounce) {
+    FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
+        RngKey key{seed, 0u, 0u, bounce};
+        if (GENERIC) batch_path(b, path, key.pixel, key.sample);
+        trace_linear_prog<false, GENERIC, NESTED, PRETEST, SHDIV>(P, S, o, d, key, w, nullptr);
+    FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------
+int launch_extend(const ExtendPlan& plan, bool use_bvh, const LinProgram& P, const DeviceScene& S, const PathState& ps,
+                  const Batch& b, uint2 seed, uint32_t bounce, cudaStream_t st) {
+    const unsigned G = ps.nseg;   // one block per segment
+    if (use_bvh && plan.has_top_mesh && plan.two_pass) {
+        if (plan.has_medium_mesh) {
+            extend_pass1_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+            extend_pass2_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+        } else {
+            extend_pass1_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+            extend_pass2_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+        }
+        return 2;
+    }
+    if (use_bvh) {
+        if (plan.has_medium_mesh)
+            extend_bvh_simple_kernel<true, true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+        else if (plan.has_mesh)
+            extend_bvh_simple_kernel<false, true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+        else
+            extend_bvh_simple_kernel<false, false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+    } else if (plan.lin_prog_ok) {
+        if (plan.lin_generic) {
+            if (plan.has_mesh)
+                extend_linear_prog_kernel<true, true, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+            else
+                extend_linear_prog_kernel<true, false, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+        } else if (plan.lin_rect_tests >= 8) {   // rectangle-heavy: shared-reciprocal division (SHDIV)
+            // coherent primary rays: whole warps skip Rect3d boxes they do not enter (PRETEST)
+            if (bounce == 0) extend_linear_prog_kernel<false, false, true, true><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+            else extend_linear_prog_kernel<false, false, false, true><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+        } else {
+            extend_linear_prog_kernel<false, false, false, false><<<G, FW_BLOCK, 0, st>>>(P, S, ps, b, seed, bounce);
+        }
+    } else if (plan.has_mesh) {
+        extend_linear_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+    } else {
+        extend_linear_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+    }
+    return 1;
+}
+void launch_extend_debug(const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce, uint32_t* steps,
+                         cudaStream_t st) {
+    extend_bvh_debug_kernel<<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, steps);
+}
+
+}  // namespace fw
