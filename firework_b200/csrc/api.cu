@@ -13,9 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/firework_b200.h"
-#include "launch.h"
-#include "scene_host.h"
+#include "api_internal.h"
 
 using namespace fw;
 
@@ -24,11 +22,6 @@ static thread_local std::string g_last_error;
 // Pinned staging for equirect HDR maps (128 MiB as float4 at 4096 x 2048): fw_scene_set_hdr expands the caller's RGB
 // texels straight into it (one multi-threaded pass), fw_scene_commit copies from it into the CUDA array.  The buffers
 // are process-wide and grow-only; a scene holds one from set_hdr until its commit / destroy.
-struct HdrStaging {
-    float* p = nullptr;
-    size_t floats = 0;
-    bool in_use = false;
-};
 static std::mutex g_staging_mutex;
 static std::vector<HdrStaging*> g_staging;
 static HdrStaging* staging_acquire(size_t floats) {
@@ -69,76 +62,18 @@ static void expand_rgb_to_rgba(const float* rgb, float* rgba, size_t texels) {
     work(0, std::min(texels, chunk));
     for (auto& t : th) t.join();
 }
-static int set_error(int code, const std::string& msg) {
+int fw::set_error(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
 int fw::set_last_error(int code, const std::string& msg) { return set_error(code, msg); }
-#define FW_CUDA(call)                                                                                         \
-    do {                                                                                                      \
-        cudaError_t e__ = (call);                                                                             \
-        if (e__ != cudaSuccess)                                                                               \
-            return set_error(FW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ \
-                                              ":" + std::to_string(__LINE__) + ")");                          \
-    } while (0)
 
 static_assert(sizeof(fw_params) == sizeof(RenderParamsHost), "fw_params layout");
 static_assert(sizeof(ShapeRec) == 48 && sizeof(MeshRec) == 64 && sizeof(MatRec) == 32 && sizeof(TexRec) == 32, "rec sizes");
 
-// Render-time device state (path-state streams, sum / image buffers, stream, events).  It is independent of the
-// scene, ~1.2 GB at the default batch size, and expensive to allocate, so contexts are cached per device and
-// handed from one fw_scene to the next (fw_release_cached_memory frees them).
-struct RenderCtx {
-    int device = 0;
-    bool in_use = false;
-    PathState ps{};
-    size_t ps_cap = 0;
-    size_t ps_nseg_max = 0;
-    cudaStream_t stream = nullptr;
-    float* d_sum = nullptr;
-    unsigned char* d_rgb = nullptr;
-    size_t d_sum_pix = 0;
-    unsigned long long* d_rays = nullptr;   // device-side ray tally of the current render call
-    unsigned long long* h_rays = nullptr;   // pinned
-    std::vector<cudaEvent_t> ev_pool;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    // Scene tables live in one device arena that the next scene on this context simply overwrites: committing and
-    // releasing a scene costs no cudaMalloc / cudaFree (each cudaFree is a device-wide synchronisation; 17 of them
-    // per scene made fw_scene_destroy take 200-500 ms inside a process that also runs torch).
-    char* arena = nullptr;
-    size_t arena_cap = 0, arena_used = 0;
-    std::vector<void*> arena_retired;   // outgrown slabs, freed when the scene that may still use them is released
-    // Texture arrays are kept for the next scene that needs the same geometry (the usual case: the same scene again).
-    struct CachedTex {
-        cudaArray_t arr = nullptr;
-        cudaTextureObject_t tex = 0;
-        uint32_t w = 0, h = 0;
-        bool is_float = false, in_use = false;
-    };
-    std::vector<CachedTex> tex_cache;
-};
 static std::mutex g_ctx_mutex;
 static std::vector<RenderCtx*> g_ctx_cache;
 
-struct fw_scene {
-    SceneDesc desc;
-    HostFlat flat;
-    uint64_t h2d_bytes = 0;  // bytes copied host->device by commit
-    bool built = false;      // host-side BVH build + flattening done
-    bool committed = false;  // uploaded to the device
-    int device = 0;
-    int sm_count = 148;
-    ExtendPlan plan;         // which extend kernel serves this scene (filled at commit)
-    DeviceScene dscene{};
-    LinProgram lin_prog{};     // linear-scan program, passed to the kernels by value (kernel-parameter space)
-    bool lin_prog_ok = false;  // the scene's program fits FW_LIN_MAX_WORDS (else: object-loop kernels)
-    bool mat_present[MAT_NUM_QUEUES] = {false, false, false, false, false, false};
-    std::vector<HdrStaging*> hdr_staging;   // per asset: pinned RGBA copy of an HDR map (set_hdr .. commit)
-    bool miss_is_zero = false;  // every escaping path contributes exactly 0: the miss kernel is not launched
-    RenderCtx* ctx = nullptr;  // render-time state, borrowed from the per-device cache at commit
-    size_t batch_paths = 0;    // 0 = default
-    bool profiling = false;
-};
 
 static int arena_alloc(fw_scene* sc, size_t bytes, void** out) {
     RenderCtx* c = sc->ctx;
@@ -246,6 +181,20 @@ static void release_device(fw_scene* sc) {
     sc->committed = false;
 }
 
+// Nothing may propagate through the C ABI: entry points that allocate run their body through this.
+template <class F>
+static int guarded(F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return set_error(FW_ERR_SCENE, "out of host memory");
+    } catch (const std::exception& e) {
+        return set_error(FW_ERR_SCENE, std::string("internal error: ") + e.what());
+    } catch (...) {
+        return set_error(FW_ERR_SCENE, "internal error");
+    }
+}
+
 namespace {
 struct DevBuf {  // tiny RAII helper for probe staging buffers
     void* p = nullptr;
@@ -279,29 +228,36 @@ int fw_device_count(void) {
 }
 
 int fw_scene_from_yaml(const char* text, size_t len, fw_scene** out) {
-    if (!text || !out) return set_error(FW_ERR_ARG, "null argument");
-    auto sc = new fw_scene();
-    std::string err;
-    if (!load_scene_yaml(text, len, sc->desc, err)) {
-        delete sc;
-        return set_error(FW_ERR_PARSE, err);
-    }
-    *out = sc;
-    return FW_OK;
+    return guarded([&]() -> int {
+        if (!text || !out) return set_error(FW_ERR_ARG, "null argument");
+        auto sc = new fw_scene();
+        std::string err;
+        if (!load_scene_yaml(text, len, sc->desc, err)) {
+            delete sc;
+            return set_error(FW_ERR_PARSE, err);
+        }
+        *out = sc;
+        return FW_OK;
+});
 }
 int fw_scene_from_file(const char* path, fw_scene** out) {
-    if (!path || !out) return set_error(FW_ERR_ARG, "null argument");
-    std::ifstream f(path, std::ios::binary);
-    if (!f) return set_error(FW_ERR_PARSE, std::string("cannot open ") + path);
-    std::stringstream ss;
-    ss << f.rdbuf();
-    std::string text = ss.str();
-    return fw_scene_from_yaml(text.data(), text.size(), out);
+    return guarded([&]() -> int {
+        if (!path || !out) return set_error(FW_ERR_ARG, "null argument");
+        std::ifstream f(path, std::ios::binary);
+        if (!f) return set_error(FW_ERR_PARSE, std::string("cannot open ") + path);
+        std::stringstream ss;
+        ss << f.rdbuf();
+        std::string text = ss.str();
+        return fw_scene_from_yaml(text.data(), text.size(), out);
+});
 }
 void fw_scene_destroy(fw_scene* sc) {
     if (!sc) return;
-    for (HdrStaging* h : sc->hdr_staging) staging_release(h);
-    release_device(sc);
+    for (fw_scene* r : sc->replicas) fw_scene_destroy(r);
+    sc->replicas.clear();
+    release_device(sc);   // synchronises the scene's stream: no upload from the staging buffers is still in flight
+    if (!sc->asset_src)
+        for (HdrStaging* h : sc->hdr_staging) staging_release(h);
     delete sc;
 }
 
@@ -315,36 +271,40 @@ int fw_scene_asset_kind(const fw_scene* sc, int i) {
     return sc->desc.assets[i].kind;
 }
 int fw_scene_set_image(fw_scene* sc, int i, uint32_t w, uint32_t h, const uint8_t* rgba) {
-    if (!sc || !rgba || i < 0 || i >= (int)sc->desc.assets.size() || w == 0 || h == 0)
-        return set_error(FW_ERR_ARG, "fw_scene_set_image: bad argument");
-    AssetDesc& a = sc->desc.assets[i];
-    if (a.kind != 0) return set_error(FW_ERR_ARG, "asset is not an image");
-    if (sc->committed) return set_error(FW_ERR_STATE, "scene already committed");
-    a.w = w; a.h = h;
-    a.rgba.assign(rgba, rgba + (size_t)w * h * 4);
-    a.provided = true;
-    return FW_OK;
+    return guarded([&]() -> int {
+        if (!sc || !rgba || i < 0 || i >= (int)sc->desc.assets.size() || w == 0 || h == 0)
+            return set_error(FW_ERR_ARG, "fw_scene_set_image: bad argument");
+        AssetDesc& a = sc->desc.assets[i];
+        if (a.kind != 0) return set_error(FW_ERR_ARG, "asset is not an image");
+        if (sc->committed) return set_error(FW_ERR_STATE, "scene already committed");
+        a.w = w; a.h = h;
+        a.rgba.assign(rgba, rgba + (size_t)w * h * 4);
+        a.provided = true;
+        return FW_OK;
+});
 }
 int fw_scene_set_hdr(fw_scene* sc, int i, uint32_t w, uint32_t h, const float* rgb) {
-    if (!sc || !rgb || i < 0 || i >= (int)sc->desc.assets.size() || w == 0 || h == 0)
-        return set_error(FW_ERR_ARG, "fw_scene_set_hdr: bad argument");
-    AssetDesc& a = sc->desc.assets[i];
-    if (a.kind != 1) return set_error(FW_ERR_ARG, "asset is not an HDR map");
-    if (sc->committed) return set_error(FW_ERR_STATE, "scene already committed");
-    a.w = w; a.h = h;
-    const size_t texels = (size_t)w * h;
-    sc->hdr_staging.resize(sc->desc.assets.size(), nullptr);
-    if (sc->hdr_staging[i]) { staging_release(sc->hdr_staging[i]); sc->hdr_staging[i] = nullptr; }
-    HdrStaging* st = staging_acquire(texels * 4);
-    if (st) {
-        expand_rgb_to_rgba(rgb, st->p, texels);
-        sc->hdr_staging[i] = st;
-        a.rgb.clear();
-    } else {
-        a.rgb.assign(rgb, rgb + texels * 3);
-    }
-    a.provided = true;
-    return FW_OK;
+    return guarded([&]() -> int {
+        if (!sc || !rgb || i < 0 || i >= (int)sc->desc.assets.size() || w == 0 || h == 0)
+            return set_error(FW_ERR_ARG, "fw_scene_set_hdr: bad argument");
+        AssetDesc& a = sc->desc.assets[i];
+        if (a.kind != 1) return set_error(FW_ERR_ARG, "asset is not an HDR map");
+        if (sc->committed) return set_error(FW_ERR_STATE, "scene already committed");
+        a.w = w; a.h = h;
+        const size_t texels = (size_t)w * h;
+        sc->hdr_staging.resize(sc->desc.assets.size(), nullptr);
+        if (sc->hdr_staging[i]) { staging_release(sc->hdr_staging[i]); sc->hdr_staging[i] = nullptr; }
+        HdrStaging* st = staging_acquire(texels * 4);
+        if (st) {
+            expand_rgb_to_rgba(rgb, st->p, texels);
+            sc->hdr_staging[i] = st;
+            a.rgb.clear();
+        } else {
+            a.rgb.assign(rgb, rgb + texels * 3);
+        }
+        a.provided = true;
+        return FW_OK;
+});
 }
 
 static int make_texture(fw_scene* sc, const void* src, uint32_t w, uint32_t h, bool is_float, cudaTextureObject_t* out) {
@@ -384,46 +344,57 @@ static int make_texture(fw_scene* sc, const void* src, uint32_t w, uint32_t h, b
 }
 
 int fw_scene_build_host(fw_scene* sc) {
-    if (!sc) return set_error(FW_ERR_ARG, "null scene");
-    if (sc->built) return FW_OK;
-    std::string err;
-    if (!flatten_scene(sc->desc, sc->flat, err)) return set_error(FW_ERR_SCENE, err);
-    sc->built = true;
-    return FW_OK;
+    return guarded([&]() -> int {
+        if (!sc) return set_error(FW_ERR_ARG, "null scene");
+        if (sc->built) return FW_OK;
+        std::string err;
+        if (!flatten_scene(sc->desc, sc->flat, err)) return set_error(FW_ERR_SCENE, err);
+        sc->built = true;
+        return FW_OK;
+});
 }
 
+static int commit_uploads(fw_scene* sc);
 int fw_scene_commit(fw_scene* sc, int device) {
-    if (!sc) return set_error(FW_ERR_ARG, "null scene");
-    if (sc->committed) return set_error(FW_ERR_STATE, "scene already committed");
-    for (const AssetDesc& a : sc->desc.assets)
-        if (!a.provided) return set_error(FW_ERR_ASSET, "asset `" + a.path + "` was not provided (fw_scene_set_image / fw_scene_set_hdr)");
-    int brc = fw_scene_build_host(sc);
-    if (brc != FW_OK) return brc;
-    int ndev = 0;
-    FW_CUDA(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return set_error(FW_ERR_CUDA, "no such CUDA device " + std::to_string(device));
-    sc->device = device;
-    FW_CUDA(cudaSetDevice(device));
-    {
-        // device facts are queried once per device (cudaGetDeviceProperties costs milliseconds)
-        static std::mutex info_mutex;
-        static int cached_sm[64];
-        static bool cached[64] = {false};
-        std::lock_guard<std::mutex> lk(info_mutex);
-        if (device < 64 && cached[device]) {
-            sc->sm_count = cached_sm[device];
-        } else {
-            int smc = 0;
-            FW_CUDA(cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device));
-            sc->sm_count = smc;
-            if (device < 64) { cached_sm[device] = sc->sm_count; cached[device] = true; }
+    return guarded([&]() -> int {
+        if (!sc) return set_error(FW_ERR_ARG, "null scene");
+        if (sc->committed) return set_error(FW_ERR_STATE, "scene already committed");
+        const fw_scene* src = sc->asset_src ? sc->asset_src : sc;
+        for (const AssetDesc& a : src->desc.assets)
+            if (!a.provided) return set_error(FW_ERR_ASSET, "asset `" + a.path + "` was not provided (fw_scene_set_image / fw_scene_set_hdr)");
+        int brc = fw_scene_build_host(sc);
+        if (brc != FW_OK) return brc;
+        int ndev = 0;
+        FW_CUDA(cudaGetDeviceCount(&ndev));
+        if (device < 0 || device >= ndev) return set_error(FW_ERR_CUDA, "no such CUDA device " + std::to_string(device));
+        sc->device = device;
+        FW_CUDA(cudaSetDevice(device));
+        {
+            // device facts are queried once per device (cudaGetDeviceProperties costs milliseconds)
+            static std::mutex info_mutex;
+            static int cached_sm[64];
+            static bool cached[64] = {false};
+            std::lock_guard<std::mutex> lk(info_mutex);
+            if (device < 64 && cached[device]) {
+                sc->sm_count = cached_sm[device];
+            } else {
+                int smc = 0;
+                FW_CUDA(cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device));
+                sc->sm_count = smc;
+                if (device < 64) { cached_sm[device] = sc->sm_count; cached[device] = true; }
+            }
         }
-    }
-    {
-        int crc = acquire_ctx(device, &sc->ctx);
-        if (crc != FW_OK) return crc;
-    }
-
+        {
+            int crc = acquire_ctx(device, &sc->ctx);
+            if (crc != FW_OK) return crc;
+        }
+        int urc = commit_uploads(sc);
+        if (urc != FW_OK) release_device(sc);   // hand the context back: a retry acquires it again
+        return urc;
+});
+}
+static int commit_uploads(fw_scene* sc) {
+    const fw_scene* src = sc->asset_src ? sc->asset_src : sc;
     DeviceScene& D = sc->dscene;
     const HostFlat& F = sc->flat;
     int rc;
@@ -436,19 +407,18 @@ int fw_scene_commit(fw_scene* sc, int device) {
     memset(&D.env, 0, sizeof(D.env));
     D.env.kind = sc->desc.env_kind;
     for (int k = 0; k < 3; ++k) { D.env.a[k] = sc->desc.env_a[k]; D.env.b[k] = sc->desc.env_b[k]; }
-    for (size_t i = 0; i < sc->desc.assets.size(); ++i) {
-        const AssetDesc& a = sc->desc.assets[i];
+    for (size_t i = 0; i < src->desc.assets.size(); ++i) {
+        const AssetDesc& a = src->desc.assets[i];
         if (a.kind == 0) {
             if ((rc = make_texture(sc, a.rgba.data(), a.w, a.h, false, &images[i].tex)) != FW_OK) return rc;
             images[i].w = a.w; images[i].h = a.h;
         } else {
             cudaTextureObject_t t;
-            HdrStaging* hs = i < sc->hdr_staging.size() ? sc->hdr_staging[i] : nullptr;
+            // the pinned staging copy stays with the scene until fw_scene_destroy: the upload below is asynchronous, and
+            // fw_render_multi replicates the scene onto other devices from it
+            HdrStaging* hs = i < src->hdr_staging.size() ? src->hdr_staging[i] : nullptr;
             if (hs) {
-                rc = make_texture(sc, hs->p, a.w, a.h, true, &t);
-                staging_release(hs);
-                sc->hdr_staging[i] = nullptr;
-                if (rc != FW_OK) return rc;
+                if ((rc = make_texture(sc, hs->p, a.w, a.h, true, &t)) != FW_OK) return rc;
             } else {
                 std::vector<float> rgba((size_t)a.w * a.h * 4);
                 expand_rgb_to_rgba(a.rgb.data(), rgba.data(), (size_t)a.w * a.h);
@@ -656,7 +626,7 @@ static int get_event(fw_scene* sc, size_t& next, cudaEvent_t* ev) {
     return FW_OK;
 }
 
-static inline unsigned grid_for(size_t n, unsigned threads, unsigned max_blocks) {
+unsigned fw::grid_for(size_t n, unsigned threads, unsigned max_blocks) {
     size_t g = (n + threads - 1) / threads;
     return (unsigned)std::max<size_t>(1, std::min<size_t>(g, max_blocks));
 }
@@ -783,7 +753,7 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
     return FW_OK;
 }
 
-static int render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStream_t st, fw_stats* stats) {
+int fw::render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStream_t st, fw_stats* stats) {
     if (!sc->committed) return set_error(FW_ERR_STATE, "fw_scene_commit must be called before rendering");
     if (!p || p->width == 0 || p->height == 0 || p->samples == 0)
         return set_error(FW_ERR_ARG, "width, height and samples must be non-zero");
@@ -846,10 +816,40 @@ static int render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStrea
     return FW_OK;
 }
 
+int fw::ensure_sum_buffers(fw_scene* sc, size_t npix) {
+    if (sc->ctx->d_sum_pix >= npix) return FW_OK;
+    if (sc->ctx->d_sum) cudaFree(sc->ctx->d_sum);
+    if (sc->ctx->d_rgb) cudaFree(sc->ctx->d_rgb);
+    sc->ctx->d_sum = nullptr; sc->ctx->d_rgb = nullptr; sc->ctx->d_sum_pix = 0;
+    FW_CUDA(cudaMalloc(&sc->ctx->d_sum, npix * 3 * sizeof(float)));
+    FW_CUDA(cudaMalloc(&sc->ctx->d_rgb, npix * 3));
+    sc->ctx->d_sum_pix = npix;
+    return FW_OK;
+}
+int fw::commit_scene(fw_scene* sc, int device) { return fw_scene_commit(sc, device); }
+void fw::destroy_scene(fw_scene* sc) { fw_scene_destroy(sc); }
+
 extern "C" {
+
+// render.rs:184-189 + util.rs:14-23 for a host sum buffer (checkpoint resume, any caller that accumulated sums itself)
+int fw_resolve_host(int device, const float* sum, uint32_t npix, uint32_t samples, float gamma, uint8_t* rgb_out) {
+    if (!sum || !rgb_out || npix == 0 || samples == 0) return set_error(FW_ERR_ARG, "bad argument");
+    int ndev = 0;
+    FW_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return set_error(FW_ERR_CUDA, "no such CUDA device " + std::to_string(device));
+    FW_CUDA(cudaSetDevice(device));
+    DevBuf s, o;
+    int rc;
+    if ((rc = s.put(sum, (size_t)npix * 12)) != FW_OK || (rc = o.alloc((size_t)npix * 3)) != FW_OK) return rc;
+    launch_resolve(s.as<float>(), npix, (float)samples, gamma, o.as<unsigned char>(), grid_for(npix, 256, 148 * 8), nullptr);
+    FW_CUDA(cudaGetLastError());
+    FW_CUDA(cudaDeviceSynchronize());
+    return o.get(rgb_out, (size_t)npix * 3);
+}
 
 int fw_render_accumulate_device(fw_scene* sc, const fw_params* p, float* d_sum, void* cuda_stream, fw_stats* stats) {
     if (!sc || !d_sum) return set_error(FW_ERR_ARG, "null argument");
+    if (!sc->committed || !sc->ctx) return set_error(FW_ERR_STATE, "fw_scene_commit must be called before rendering");
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : sc->ctx->stream;
     return render_into(sc, p, d_sum, st, stats);
 }
@@ -866,31 +866,27 @@ int fw_resolve_device(fw_scene* sc, const float* d_sum, uint32_t npix, uint32_t 
 }
 
 int fw_render(fw_scene* sc, const fw_params* p, uint8_t* rgb_out, float* sum_out, fw_stats* stats) {
-    if (!sc || !p) return set_error(FW_ERR_ARG, "null argument");
-    if (!sc->committed) return set_error(FW_ERR_STATE, "fw_scene_commit must be called before rendering");
-    FW_CUDA(cudaSetDevice(sc->device));
-    size_t npix = (size_t)p->width * p->height;
-    if (npix == 0) return set_error(FW_ERR_ARG, "empty image");
-    if (sc->ctx->d_sum_pix < npix) {
-        if (sc->ctx->d_sum) cudaFree(sc->ctx->d_sum);
-        if (sc->ctx->d_rgb) cudaFree(sc->ctx->d_rgb);
-        sc->ctx->d_sum = nullptr; sc->ctx->d_rgb = nullptr; sc->ctx->d_sum_pix = 0;
-        FW_CUDA(cudaMalloc(&sc->ctx->d_sum, npix * 3 * sizeof(float)));
-        FW_CUDA(cudaMalloc(&sc->ctx->d_rgb, npix * 3));
-        sc->ctx->d_sum_pix = npix;
-    }
-    FW_CUDA(cudaMemsetAsync(sc->ctx->d_sum, 0, npix * 3 * sizeof(float), sc->ctx->stream));
-    int rc = render_into(sc, p, sc->ctx->d_sum, sc->ctx->stream, stats);
-    if (rc != FW_OK) return rc;
-    if (rgb_out) {
-        launch_resolve(sc->ctx->d_sum, (uint32_t)npix, (float)p->samples, p->gamma, sc->ctx->d_rgb, grid_for(npix, 256, sc->sm_count * 8), sc->ctx->stream);
-        FW_CUDA(cudaGetLastError());
-        if (stats) stats->launches++;
-        FW_CUDA(cudaMemcpyAsync(rgb_out, sc->ctx->d_rgb, npix * 3, cudaMemcpyDeviceToHost, sc->ctx->stream));
-    }
-    if (sum_out) FW_CUDA(cudaMemcpyAsync(sum_out, sc->ctx->d_sum, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, sc->ctx->stream));
-    FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
-    return FW_OK;
+    return guarded([&]() -> int {
+        if (!sc || !p) return set_error(FW_ERR_ARG, "null argument");
+        if (!sc->committed) return set_error(FW_ERR_STATE, "fw_scene_commit must be called before rendering");
+        FW_CUDA(cudaSetDevice(sc->device));
+        size_t npix = (size_t)p->width * p->height;
+        if (npix == 0) return set_error(FW_ERR_ARG, "empty image");
+        int brc = ensure_sum_buffers(sc, npix);
+        if (brc != FW_OK) return brc;
+        FW_CUDA(cudaMemsetAsync(sc->ctx->d_sum, 0, npix * 3 * sizeof(float), sc->ctx->stream));
+        int rc = render_into(sc, p, sc->ctx->d_sum, sc->ctx->stream, stats);
+        if (rc != FW_OK) return rc;
+        if (rgb_out) {
+            launch_resolve(sc->ctx->d_sum, (uint32_t)npix, (float)p->samples, p->gamma, sc->ctx->d_rgb, grid_for(npix, 256, sc->sm_count * 8), sc->ctx->stream);
+            FW_CUDA(cudaGetLastError());
+            if (stats) stats->launches++;
+            FW_CUDA(cudaMemcpyAsync(rgb_out, sc->ctx->d_rgb, npix * 3, cudaMemcpyDeviceToHost, sc->ctx->stream));
+        }
+        if (sum_out) FW_CUDA(cudaMemcpyAsync(sum_out, sc->ctx->d_sum, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, sc->ctx->stream));
+        FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
+        return FW_OK;
+});
 }
 
 // ---- probes ---------------------------------------------------------------------------------------------

@@ -56,8 +56,18 @@ extern "C" {
 // tobj::load_obj: every `o` / `g` statement (and a material change) closes the model gathered so far; faces are
 // fan-triangulated ((0,1,2), (0,2,3), ...); vertices are re-indexed per model so that each distinct v/vt/vn triple
 // becomes one vertex, in order of first use.
+static int obj_load_impl(const char* path, fw_obj** out);
 int fw_obj_load(const char* path, fw_obj** out) {
     if (!path || !out) return fw::set_last_error(FW_ERR_ARG, "null argument");
+    try {   // nothing may propagate through the C ABI
+        return obj_load_impl(path, out);
+    } catch (const std::exception& e) {
+        return fw::set_last_error(FW_ERR_PARSE, std::string(path) + ": " + e.what());
+    } catch (...) {
+        return fw::set_last_error(FW_ERR_PARSE, std::string(path) + ": internal error");
+    }
+}
+static int obj_load_impl(const char* path, fw_obj** out) {
     std::ifstream f(path);
     if (!f) return fw::set_last_error(FW_ERR_PARSE, std::string("cannot open ") + path);
     std::vector<float> pos, nrm, tex;
@@ -199,10 +209,19 @@ int fw_hdr_load(const char* path, uint32_t* w_out, uint32_t* h_out, float** rgb_
     if (!read_line(line)) return fail("missing resolution line");
     long hh = 0, ww = 0;
     if (sscanf(line.c_str(), "-Y %ld +X %ld", &hh, &ww) != 2 || hh <= 0 || ww <= 0) return fail("unsupported orientation `" + line + "`");
+    // a header is untrusted input: bound the size before any allocation (65536 x 65536 x 12 B would already be 48 GiB)
+    if (ww > 65536 || hh > 65536 || (unsigned long long)ww * (unsigned long long)hh > (1ull << 28))
+        return fail("unreasonable image size " + std::to_string(ww) + " x " + std::to_string(hh));
     const size_t w = (size_t)ww, h = (size_t)hh;
     float* rgb = (float*)malloc(w * h * 3 * sizeof(float));
     if (!rgb) return fail("out of memory");
-    std::vector<unsigned char> scan(w * 4);
+    std::vector<unsigned char> scan;
+    try {
+        scan.resize(w * 4);
+    } catch (const std::exception&) {   // nothing may propagate through the C ABI
+        free(rgb);
+        return fail("out of memory");
+    }
     for (size_t y = 0; y < h; ++y) {
         unsigned char head[4];
         if (fread(head, 1, 4, f) != 4) { free(rgb); return fail("truncated pixel data"); }

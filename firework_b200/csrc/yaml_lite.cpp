@@ -68,7 +68,10 @@ struct Parser {
         }
     }
     // value inside a flow collection or as a whole line; `stops` = extra terminators in flow context
-    bool parse_flow_value(const char*& p, const char* e, Node& n, int line, bool in_flow) {
+    // Flow collections nest by recursion; a hostile document ("[[[[...") must not be able to exhaust the stack.
+    static constexpr int kMaxFlowDepth = 64;
+    bool parse_flow_value(const char*& p, const char* e, Node& n, int line, bool in_flow, int depth = 0) {
+        if (depth > kMaxFlowDepth) return fail(line, "flow collections nested too deeply");
         skip_ws(p, e);
         n.line = line;
         if (p >= e) { n.kind = Node::NUL; return true; }
@@ -79,7 +82,7 @@ struct Parser {
             if (p < e && *p == ']') { ++p; return true; }
             for (;;) {
                 Node item;
-                if (!parse_flow_value(p, e, item, line, true)) return false;
+                if (!parse_flow_value(p, e, item, line, true, depth + 1)) return false;
                 n.seq.push_back(std::move(item));
                 skip_ws(p, e);
                 if (p < e && *p == ',') { ++p; continue; }
@@ -108,7 +111,7 @@ struct Parser {
                 if (p >= e || *p != ':') return fail(line, "expected ':' in flow mapping");
                 ++p;
                 Node val;
-                if (!parse_flow_value(p, e, val, line, true)) return false;
+                if (!parse_flow_value(p, e, val, line, true, depth + 1)) return false;
                 n.map.emplace_back(std::move(key), std::move(val));
                 skip_ws(p, e);
                 if (p < e && *p == ',') { ++p; continue; }

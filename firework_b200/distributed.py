@@ -40,8 +40,25 @@ def render_sharded(render_shard: Callable[[int, int], "object"], resolve: Callab
     return None, total
 
 
+def stream_scope(renderer_obj):
+    """Context manager that makes `renderer_obj.stream` torch's current stream (a no-op for CPU stand-ins)."""
+    import contextlib
+    st = getattr(renderer_obj, "stream", None)
+    if st is None:
+        return contextlib.nullcontext()
+    import torch
+    return torch.cuda.stream(st)
+
+
 class GpuShardRenderer:
-    """render_shard / resolve for one rank on its own GPU, through the C ABI's device-resident entry points."""
+    """render_shard / resolve for one rank on its own GPU, through the C ABI's device-resident entry points.
+
+    Stream ordering: every piece of device work of a step — the zero-fill of the sum buffer, the render kernels, the
+    NCCL reduce, the resolve kernel and the device->host copy of the image — is issued on ONE explicit, non-default
+    torch stream (`self.stream`), made current with `use_stream()` around the whole step.  Passing torch's default
+    stream would not work: its handle is 0, which the C ABI reads as "use the scene's private stream", and that stream
+    has no ordering against the stream torch / NCCL use (the resolve would read the buffer before the reduce wrote it).
+    """
 
     def __init__(self, native_scene, renderer, device_index: int):
         import torch
@@ -49,24 +66,35 @@ class GpuShardRenderer:
         self.ns = native_scene
         self.renderer = renderer
         self.device = torch.device("cuda", device_index)
+        self.stream = torch.cuda.Stream(self.device)
+        assert self.stream.cuda_stream != 0
         p = renderer.params()
         self.npix = p.width * p.height
         self.shape = (p.height, p.width, 3)
         self.last_stats = None
 
+    def use_stream(self):
+        return self.torch.cuda.stream(self.stream)
+
     def render_shard(self, begin: int, count: int):
         torch = self.torch
-        d_sum = torch.zeros(self.npix * 3, dtype=torch.float32, device=self.device)
-        if count > 0:
-            p = self.renderer.params(sample_begin=begin, sample_count=count)
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            self.last_stats = self.ns.render_accumulate_device(p, d_sum.data_ptr(), stream)
+        with self.use_stream():
+            d_sum = torch.zeros(self.npix * 3, dtype=torch.float32, device=self.device)
+            if count > 0:
+                p = self.renderer.params(sample_begin=begin, sample_count=count)
+                self.last_stats = self.ns.render_accumulate_device(p, d_sum.data_ptr(), self.stream.cuda_stream)
         return d_sum
 
     def resolve(self, d_sum):
         torch = self.torch
         p = self.renderer.params()
-        d_rgb = torch.empty(self.npix * 3, dtype=torch.uint8, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        self.ns.resolve_device(d_sum.data_ptr(), self.npix, p.samples, p.gamma, d_rgb.data_ptr(), stream)
-        return d_rgb.cpu().numpy().reshape(self.shape)
+        with self.use_stream():
+            d_rgb = torch.empty(self.npix * 3, dtype=torch.uint8, device=self.device)
+            self.ns.resolve_device(d_sum.data_ptr(), self.npix, p.samples, p.gamma, d_rgb.data_ptr(), self.stream.cuda_stream)
+            out = d_rgb.cpu()          # same stream: ordered after the resolve kernel, synchronises it
+        return out.numpy().reshape(self.shape)
+
+    def render(self, samples: int, rank: int, world: int):
+        """One sharded render step: (image on rank 0 | None, this rank's / the reduced sum tensor)."""
+        with self.use_stream():    # dist.reduce orders itself against torch's CURRENT stream
+            return render_sharded(self.render_shard, self.resolve, samples, rank, world)

@@ -126,6 +126,23 @@ class NativeScene:
                                   N.ptr(s) if want_sum else None, C.byref(st)))
         return rgb, s, st.as_dict()
 
+    def render_multi(self, params: N.FwParams, n_gpus: int, devices=None, reduce="nccl", want_rgb=True, want_sum=True):
+        """fw_render_multi: the call's sample range split over `n_gpus` devices of this box (single process), sums
+        combined on this scene's device by one NCCL reduce (`reduce="nccl"`) or by the fused peer-memory
+        reduce + resolve kernel (`reduce="peer"`).  Returns (rgb | None, total sum | None, stats dict)."""
+        h, w = params.height, params.width
+        rgb = np.empty((h, w, 3), np.uint8) if want_rgb else None
+        s = np.empty((h, w, 3), np.float32) if want_sum else None
+        st = N.FwStats()
+        ms = C.c_double()
+        dev = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        N.check(N.lib().fw_render_multi(self._h, C.byref(params), int(n_gpus), None if dev is None else N.ptr(dev),
+                                        {"nccl": 0, "peer": 1}[reduce], N.ptr(rgb) if want_rgb else None,
+                                        N.ptr(s) if want_sum else None, C.byref(st), C.byref(ms)))
+        d = st.as_dict()
+        d["ms_reduce"] = ms.value
+        return rgb, s, d
+
     def render_accumulate_device(self, params: N.FwParams, d_sum_ptr: int, stream_ptr: int = 0):
         """Adds the params' sample range into a device fp32 buffer (e.g. a torch tensor's data_ptr())."""
         st = N.FwStats()
@@ -206,6 +223,14 @@ def selftest_shared_division(n_pairs: int, seed: int = 1, device: int = 0):
     v = np.zeros(2, np.uint64)
     N.check(N.lib().fw_selftest_shared_division(device, C.c_uint64(n_pairs), C.c_uint64(seed), N.ptr(v)))
     return int(v[0]), int(v[1])
+
+
+def resolve_host(sums: np.ndarray, samples: int, gamma: float, device: int = 0) -> np.ndarray:
+    """render.rs:184-189 for a host fp32 sum buffer (H, W, 3) -> u8 image, on the GPU (fw_resolve_host)."""
+    s = np.ascontiguousarray(sums, np.float32)
+    out = np.empty(s.shape, np.uint8)
+    N.check(N.lib().fw_resolve_host(device, N.ptr(s), s.size // 3, int(samples), C.c_float(gamma), N.ptr(out)))
+    return out
 
 
 def render_scene(scene, renderer, device: int = 0):

@@ -11,7 +11,21 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from .engine import NativeScene
+import hashlib
+
+from .engine import NativeScene, resolve_host
+
+
+def render_fingerprint(scene, renderer) -> str:
+    """Identifies WHAT is being rendered: the scene document and every renderer / camera parameter except the sample
+    count (the sums are un-normalised, so a render may be resumed towards a LARGER total; a smaller one is refused).
+    A checkpoint may only be resumed by the render that wrote it."""
+    p = renderer.params()
+    h = hashlib.sha256()
+    h.update(scene.to_yaml().encode("utf-8"))
+    h.update(repr((p.width, p.height, p.use_bvh, p.gamma, tuple(p.cam_pos), tuple(p.look_at), p.vfov,
+                   p.aperture, p.focus_dist, p.seed)).encode())
+    return h.hexdigest()
 
 
 def render_progressive(scene, renderer, checkpoint: Optional[str] = None, chunk: int = 64, device: int = 0,
@@ -22,11 +36,14 @@ def render_progressive(scene, renderer, checkpoint: Optional[str] = None, chunk:
     h, w, total = p0.height, p0.width, p0.samples
     done = 0
     sums = np.zeros((h, w, 3), np.float32)
+    fp = render_fingerprint(scene, renderer)
     if checkpoint and os.path.exists(checkpoint):
         ck = np.load(checkpoint)
-        if ck["sums"].shape != sums.shape or int(ck["seed"]) != p0.seed:
-            raise ValueError("checkpoint does not match this render (size or seed)")
+        if "fingerprint" not in ck.files or str(ck["fingerprint"]) != fp or ck["sums"].shape != sums.shape:
+            raise ValueError("checkpoint does not match this render (scene, camera, renderer parameters or size differ)")
         sums, done = ck["sums"].astype(np.float32), int(ck["done"])
+        if not (0 <= done <= total):
+            raise ValueError(f"checkpoint holds {done} samples but this render has {total}")
     ns = NativeScene.from_scene(scene, device)
     rays = 0
     try:
@@ -38,22 +55,12 @@ def render_progressive(scene, renderer, checkpoint: Optional[str] = None, chunk:
             rays += st["rays"]
             if checkpoint:
                 tmp = checkpoint + ".tmp.npz"
-                np.savez(tmp, sums=sums, done=done, seed=p0.seed)
+                np.savez(tmp, sums=sums, done=done, seed=p0.seed, fingerprint=fp)
                 os.replace(tmp, checkpoint)
             if on_step:
                 on_step(done, total)
-        # resolve (render.rs:184-189) on the device from the accumulated sums
-        rgb = resolve_sums(ns, sums, done if done else 1, p0.gamma)
+        # resolve (render.rs:184-189) on the device from the accumulated sums (fw_resolve_host: no torch involved)
+        rgb = resolve_host(sums, done if done else 1, p0.gamma, device)
     finally:
         ns.close()
     return rgb, {"samples_done": done, "rays": rays}
-
-
-def resolve_sums(ns: NativeScene, sums: np.ndarray, samples: int, gamma: float) -> np.ndarray:
-    import torch
-    d = torch.from_numpy(np.ascontiguousarray(sums, np.float32)).reshape(-1).cuda(ns.device)
-    out = torch.empty(d.numel(), dtype=torch.uint8, device=d.device)
-    ns.resolve_device(d.data_ptr(), d.numel() // 3, samples, gamma, out.data_ptr(),
-                      torch.cuda.current_stream(d.device).cuda_stream)
-    torch.cuda.synchronize(d.device)
-    return out.cpu().numpy().reshape(sums.shape)

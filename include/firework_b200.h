@@ -113,6 +113,26 @@ int fw_render_accumulate_device(fw_scene* scene, const fw_params* params, float*
 int fw_resolve_device(fw_scene* scene, const float* d_sum, uint32_t npix, uint32_t samples, float gamma,
                       uint8_t* d_rgb, void* cuda_stream);
 
+/* The same resolve for a HOST sum buffer (e.g. sums accumulated by the caller across checkpointed render calls);
+ * runs on `device`, needs no scene. */
+int fw_resolve_host(int device, const float* sum, uint32_t npix, uint32_t samples, float gamma, uint8_t* rgb_out);
+
+/* ---- one render call over several GPUs of one box (single process) ------------------------------------------
+ * replaces: the same loop (src/render.rs:123-196); the reference has no multi-device path.  The call's sample range
+ * [sample_begin, sample_begin + sample_count) is split into n_gpus contiguous slices; device i renders every pixel for
+ * slice i (own host thread, own stream, own replica of the scene, created on first use), the fp32 sum buffers are
+ * combined on devices[0] and resolved there.  `devices` lists the CUDA devices to use (NULL: the scene's device first,
+ * then the lowest-numbered others); devices[0] must be the device the scene was committed on.
+ * reduce_mode FW_REDUCE_NCCL: one ncclReduce(sum, fp32, root 0) over NVLink (libnccl.so.2 is loaded on first use);
+ *             FW_REDUCE_PEER: one kernel on devices[0] reads the peers' buffers through NVLink peer mappings, sums them
+ *             in rank order and resolves in the same pass.
+ * rgb_out / sum_out as fw_render (sum_out receives the TOTAL over all devices).  ms_reduce (nullable): CUDA-event time
+ * of the combine + resolve step on devices[0].  stats: samples / rays / launches summed over devices, ms_device = the
+ * slowest device + the combine step. */
+enum { FW_REDUCE_NCCL = 0, FW_REDUCE_PEER = 1 };
+int fw_render_multi(fw_scene* scene, const fw_params* params, int n_gpus, const int* devices, int reduce_mode,
+                    uint8_t* rgb_out, float* sum_out, fw_stats* stats, double* ms_reduce);
+
 /* ---- probe entry points for the parity gates (host buffers) -----------------------------------------------
  * fw_primary_rays : camera.rs:109-116 + render.rs:173-180 for sample index `sample`, pixels [pix_begin, +n).
  * fw_first_hit    : render.rs:19 `root.hit(r, 0.001, 2e9, rng)`; obj = -1 on miss. pixel/sample/bounce key

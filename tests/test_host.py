@@ -9,7 +9,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ALL_SCENES, REPO, native_scene, oracle_scene, scene_doc, scene_text
+from conftest import ALL_SCENES, CONFIGS, REPO, native_scene, oracle_scene, params_for, scene_doc, scene_text
 from firework_b200 import _native as N
 from firework_b200.engine import NativeScene
 from firework_b200.serde_yaml import dumps, loads
@@ -303,3 +303,52 @@ def test_reclustered_bvh_keeps_the_references_leaves(name):
     assert set(ref) == {str(k) for k in leaves}
     for k, (lo, hi) in leaves.items():
         assert np.array_equal(np.array(ref[str(k)][0], np.float32), lo) and np.array_equal(np.array(ref[str(k)][1], np.float32), hi)
+
+
+def test_hostile_inputs_are_rejected_not_crashed(tmp_path):
+    """Untrusted inputs must come back as error codes: deeply nested flow YAML (recursion), a Radiance header claiming an
+    absurd size (allocation overflow), a render call on a scene that was never committed (no context to read)."""
+    import ctypes as C
+    from firework_b200._native import FireworkError, FwParams, FwStats
+    from firework_b200.assets import load_hdr
+    from firework_b200.engine import NativeScene
+    with pytest.raises(FireworkError, match="nested too deeply"):
+        NativeScene("render_objects: " + "[" * 100000 + "]" * 100000 + "\nmaterials: []\n", commit=False)
+    big = tmp_path / "big.hdr"
+    big.write_bytes(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2147483648 +X 2147483648\n" + b"\0" * 64)
+    with pytest.raises(FireworkError, match="unreasonable image size"):
+        load_hdr(str(big))
+    from conftest import params_for
+    ns = native_scene("cornell_box", commit=False)
+    p = params_for("cornell_box", 8, 8, 1)
+    st = FwStats()
+    rc = N.lib().fw_render_accumulate_device(ns._h, C.byref(p), C.c_void_p(16), None, C.byref(st))
+    assert rc == -6 and b"commit" in N.lib().fw_last_error()          # FW_ERR_STATE, not a crash
+    rc = N.lib().fw_render_multi(ns._h, C.byref(p), 2, None, 0, None, None, C.byref(st), None)
+    assert rc == -6
+    ns.close()
+
+
+def test_static_library_is_built_beside_the_shared_one():
+    """BASELINE.json north_star: "a CUDA static library built by build.rs" — the archive a Rust host would link."""
+    import subprocess
+    from firework_b200.build import STATIC_LIB
+    assert os.path.exists(STATIC_LIB)
+    members = subprocess.run(["ar", "t", STATIC_LIB], capture_output=True, text=True, check=True).stdout.split()
+    assert {"api.o", "kernels_extend.o", "kernels_shade.o", "scene_host.o", "multi_gpu.o"} <= set(members)
+    syms = subprocess.run(["nm", "-g", "--defined-only", STATIC_LIB], capture_output=True, text=True, check=True).stdout
+    for name in ("fw_scene_from_yaml", "fw_render", "fw_render_multi"):
+        assert re.search(rf"\bT {name}\b", syms), name
+
+
+def test_checkpoint_fingerprint_guards_resume(tmp_path):
+    """A checkpoint may only be resumed by the render that wrote it (same scene / camera / renderer parameters)."""
+    from firework_b200.api import Scene
+    from firework_b200.progressive import render_fingerprint
+    a = Scene.from_file(CONFIGS["cornell_box"].path())
+    b = Scene.from_file(CONFIGS["volume"].path())
+    ra = CONFIGS["cornell_box"].renderer(width=16, height=16, samples=4, seed=1)
+    assert render_fingerprint(a, ra) == render_fingerprint(a, CONFIGS["cornell_box"].renderer(width=16, height=16, samples=9, seed=1))
+    assert render_fingerprint(a, ra) != render_fingerprint(b, ra)
+    assert render_fingerprint(a, ra) != render_fingerprint(a, CONFIGS["cornell_box"].renderer(width=16, height=16, samples=4, seed=2))
+    assert render_fingerprint(a, ra) != render_fingerprint(a, CONFIGS["cornell_box"].renderer(width=17, height=16, samples=4, seed=1))
