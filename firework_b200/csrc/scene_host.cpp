@@ -967,6 +967,28 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         m.w = obj;
         out.leaf_meta.push_back(m);
     }
+    {
+        out.top_wide_depth = top.wide_depth;
+        out.mesh_wide_depth = max_mesh_wide_depth;
+        int max_prim = 0;
+        bool roots_wide = top.root_code >= 0;
+        for (const ObjectDesc& o : desc.objects) {
+            const ShapeRec& sh = desc.shapes[o.shape];
+            if (sh.kind == SH_MESH) {
+                out.n_top_meshes++;
+                max_prim = std::max(max_prim, out.meshes[sh.i0].tri_count - 1);
+                roots_wide = roots_wide && out.meshes[sh.i0].root_code >= 0;
+            } else if (sh.kind == SH_RECT3D) {
+                max_prim = std::max(max_prim, sh.i1 - 1);
+            }
+        }
+        int rank_bits = 1;
+        while (rank_bits < 31 && ((size_t)1 << rank_bits) < desc.objects.size()) ++rank_bits;
+        out.walk_prim_bits = 32 - rank_bits;
+        const bool key_fits = (size_t)max_prim < ((size_t)1 << out.walk_prim_bits) && ((size_t)1 << rank_bits) >= desc.objects.size();
+        out.walk_ok = roots_wide && key_fits && out.n_top_meshes <= 8 && 3 * top.wide_depth + 4 <= 64 &&
+                      3 * max_mesh_wide_depth + 4 <= 64;
+    }
     out.top_depth = top.max_depth;
     out.top_nodes = (int)(top.nodes.size() / 8);
     out.nodes = top.nodes;

@@ -97,6 +97,12 @@ struct HostFlat {
     bool has_mesh = false;          // some object is (or wraps) a TriangleMesh
     bool has_top_mesh = false;      // some render object IS a TriangleMesh
     bool has_medium_mesh = false;   // some ConstantMedium wraps a TriangleMesh
+    // Collect / test walk kernels (walk.cuh): usable when both roots are wide nodes, the per-lane stack bounds hold, the
+    // scene has few enough top-level meshes for the entry queue, and (t, rank, primitive) packs into one 64-bit key.
+    int top_wide_depth = 0, mesh_wide_depth = 0;
+    int n_top_meshes = 0;           // render objects that ARE a TriangleMesh
+    int walk_prim_bits = 0;         // key = t bits << 32 | ~rank << prim_bits | ~prim
+    bool walk_ok = false;
 };
 bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err);
 

@@ -1,0 +1,117 @@
+// Collect / test traversal for BVH scenes (Renderer.use_bvh == true): the closest-hit query of render.rs:19 ->
+// bvh.rs:115-151 restructured so that every instruction of the hot loop is useful for (almost) every lane of a warp.
+//
+// The lock-step kernels (kernels_extend.cu) run "walk to a leaf, test its items, pop" per lane; lanes of a warp are in
+// different phases, so box code ran with ~6-8 of 32 lanes on mesh walks and ~18 on sphere scenes (ncu, profiles/r01f).
+// Here the three phases are separated:
+//   WALK   one loop iteration = one wide-node visit for every lane that has a ray (pop, four slab tests with the
+//          reference's arithmetic aabb.rs:30-50, push the surviving interior children).  Surviving LEAF children are not
+//          tested; the lane appends (lane, leaf) pairs to a small per-warp buffer in shared memory.
+//   TEST   whenever the buffer holds 32 pairs the whole warp tests them, one pair per lane: the ray is fetched from the
+//          owning lane's slot in shared memory, the leaf's 1-2 items go through the ordinary shape routines
+//          (objects/*.rs restated in intersect.cuh), and hits are merged into the owning ray's 64-bit key with
+//          atomicMin — key = (t bits, ~rank, ~primitive), i.e. exactly "smallest t, ties to the later leaf"
+//          (bvh.rs:128,141).  The walking lane reads its key for the culling bound, so culling is only delayed by a few
+//          iterations, never wrong (a culled subtree can not hold the winner).
+//   REFILL warps are persistent inside their segment: when enough lanes have run out of nodes the warp flushes its
+//          pairs, retires the finished rays and fetches new ones from the segment's queue (shared cursor).  With no
+//          item / enter / exit code left inside the walk loop, refilled lanes do not serialise against the others (the
+//          reason refilling did not pay for the lock-step kernels, profiles/r01_extend_variants.md).
+// TriangleMesh objects are a second instance of the same machine: the top-level test phase runs the mesh's root-box test
+// (scene.rs:242-253 + bvh.rs:117) and emits (ray, mesh) ENTRIES; walk_mesh_kernel walks one mesh tree per entry in the
+// mesh's object space, tests triangles (mesh.rs:140-219) in its test phase and merges into the same per-ray key in
+// global memory; classify_kernel then sorts the rays into the shade queues.  The barycentrics of the winning triangle
+// are recomputed by finalize_hit (same arithmetic, once per ray) instead of travelling through the queues.
+#pragma once
+#include "wavefront.cuh"
+
+namespace fw {
+
+#ifndef FW_WALK_MIN_BLOCKS
+#define FW_WALK_MIN_BLOCKS 6      // __launch_bounds__ min blocks / SM of the walk kernels (register cap knob)
+#endif
+#ifndef FW_WALK_REFILL_IDLE
+#define FW_WALK_REFILL_IDLE 12    // refill a warp when at least this many of its lanes have no node left to visit
+#endif
+constexpr int FW_WALK_STACK = 64;      // deferred interior children per lane (3 per wide level; checked at flatten)
+constexpr int FW_WALK_PAIRS = 160;     // < 32 left over + at most 4 new per lane
+constexpr int FW_WALK_WARPS = FW_BLOCK / 32;
+constexpr unsigned long long FW_KEY_NONE = ~0ull;
+
+// key = t bits << 32 | ~rank << prim_bits | ~prim: atomicMin keeps the smallest t, then the largest rank, then the
+// largest primitive slot — the merge rule of bvh.rs:120-146 as a total order (t > 0 always: t_min = 0.001).
+FW_DEV unsigned long long pack_key(float t, int rank, int prim, int prim_bits) {
+    uint32_t lo = ((uint32_t)(~rank) << prim_bits) | ((uint32_t)(~prim) & ((1u << prim_bits) - 1u));
+    return ((unsigned long long)__float_as_uint(t) << 32) | lo;
+}
+FW_DEV float key_t(unsigned long long k) { return __uint_as_float((uint32_t)(k >> 32)); }
+FW_DEV int key_rank(unsigned long long k, int prim_bits) { return (int)((~(uint32_t)k) >> prim_bits); }
+FW_DEV int key_prim(unsigned long long k, int prim_bits) { return (int)((~(uint32_t)k) & ((1u << prim_bits) - 1u)); }
+FW_DEV float key_bound(unsigned long long k) { return k == FW_KEY_NONE ? FW_FLT_MAX : cull_bound(key_t(k)); }
+
+// Per-warp scratch in shared memory: the rays the warp currently owns (read by whichever lane tests one of their
+// pairs), their keys, and the pair buffer.
+struct WalkWarp {
+    unsigned long long key[32];
+    float ox[32], oy[32], oz[32], dx[32], dy[32], dz[32];
+    uint32_t a0[32], a1[32];        // top level: path, -      mesh level: first triangle slot of the mesh, rank
+    float su_x[32], su_y[32], su_z[32];
+    int su_k[32];                   // mesh level: TriSetup of the ray in the mesh's space (mesh.rs:146-163)
+    uint32_t pairs[FW_WALK_PAIRS];  // (~leaf code) << 5 | owning lane
+};
+
+struct WalkAux {
+    unsigned long long* tkey;   // [nseg][seg_cap] per-ray key of the current bounce (mesh scenes)
+    uint2* entries;             // [nseg][ent_cap] (slot in the segment's extend queue, top-level rank of the mesh)
+    uint32_t ent_cap;           // entries per segment
+    int prim_bits;
+};
+
+// One wide-node visit for the walk loop.  Children that survive the slab test and the distance cull are split into
+// leaves (returned in l0..l3 for the caller to emit) and interior nodes (nearest becomes `node`, the rest are pushed).
+FW_DEV void walk_visit(const float4* __restrict__ nodes, int& node, float3 o, float3 inv, float bound, int* stk_code,
+                       float* stk_te, int& sp, bool& l0, bool& l1, bool& l2, bool& l3, int4& cc) {
+    const float tmin = 0.001f, tmax = 2e9f;   // render.rs:19
+    const float4* n = &nodes[8 * node];
+    const unsigned sx = inv.x < 0.0f ? 48u : 0u, sy = inv.y < 0.0f ? 48u : 0u, sz = inv.z < 0.0f ? 48u : 0u;
+    const uintptr_t nb = reinterpret_cast<uintptr_t>(n);
+    auto row = [nb](unsigned byte_off) { return reinterpret_cast<const float4*>(nb | (uintptr_t)byte_off); };
+    float4 nx = __ldg(row(sx)), ny = __ldg(row(16u + sy)), nz = __ldg(row(32u + sz));
+    float4 fx = __ldg(row(48u - sx)), fy = __ldg(row(64u - sy)), fz = __ldg(row(80u - sz));
+    cc = __ldg(reinterpret_cast<const int4*>(n + 6));
+    float t0, t1, t2, t3;
+    bool h0 = slab_near_far(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, o, inv, tmin, tmax, t0);
+    bool h1 = slab_near_far(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, o, inv, tmin, tmax, t1);
+    bool h2 = slab_near_far(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, o, inv, tmin, tmax, t2);
+    bool h3 = slab_near_far(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, o, inv, tmin, tmax, t3);
+    h0 = h0 && !(t0 > bound); h1 = h1 && !(t1 > bound); h2 = h2 && !(t2 > bound); h3 = h3 && !(t3 > bound);
+    l0 = h0 && cc.x < 0; l1 = h1 && cc.y < 0; l2 = h2 && cc.z < 0; l3 = h3 && cc.w < 0;   // empty slots never pass the slab test
+    const float miss = __int_as_float(0x7f800000);
+    t0 = (h0 && cc.x >= 0) ? t0 : miss; t1 = (h1 && cc.y >= 0) ? t1 : miss;
+    t2 = (h2 && cc.z >= 0) ? t2 : miss; t3 = (h3 && cc.w >= 0) ? t3 : miss;
+    int c0 = cc.x, c1 = cc.y, c2 = cc.z, c3 = cc.w;
+    cswap(t0, c0, t1, c1);
+    cswap(t2, c2, t3, c3);
+    cswap(t0, c0, t2, c2);   // (t0, c0) = nearest surviving interior child
+    if (t3 < miss) { stk_code[sp] = c3; stk_te[sp] = t3; ++sp; }
+    if (t2 < miss) { stk_code[sp] = c2; stk_te[sp] = t2; ++sp; }
+    if (t1 < miss) { stk_code[sp] = c1; stk_te[sp] = t1; ++sp; }
+    node = (t0 < miss) ? c0 : -1;
+}
+
+// Appends the leaf children a lane found (l0..l3 of cc) to the warp's pair buffer; returns the new pair count.
+// All 32 lanes must call (lanes without work pass false flags).
+FW_DEV int walk_emit(WalkWarp& W, int npairs, bool l0, bool l1, bool l2, bool l3, int4 cc) {
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const int c = (int)l0 + (int)l1 + (int)l2 + (int)l3;
+    const unsigned b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2), b2 = __ballot_sync(0xffffffffu, c & 4);
+    if ((b0 | b1 | b2) == 0u) return npairs;
+    int off = npairs + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+    if (l0) W.pairs[off++] = ((uint32_t)(~cc.x) << 5) | lane;
+    if (l1) W.pairs[off++] = ((uint32_t)(~cc.y) << 5) | lane;
+    if (l2) W.pairs[off++] = ((uint32_t)(~cc.z) << 5) | lane;
+    if (l3) W.pairs[off++] = ((uint32_t)(~cc.w) << 5) | lane;
+    return npairs + __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+}
+
+}  // namespace fw

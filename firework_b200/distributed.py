@@ -23,31 +23,27 @@ def shard_range(samples: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def render_sharded(render_shard: Callable[[int, int], "object"], resolve: Callable[["object"], np.ndarray],
-                   samples: int, rank: int, world: int, reduce_fn: Optional[Callable[["object"], None]] = None):
+                   samples: int, rank: int, world: int, reduce_fn: Optional[Callable[["object"], None]] = None,
+                   reduce_events=None):
     """Generic driver. `render_shard(begin, count)` returns this rank's fp32 sum tensor (any torch device);
     `reduce_fn(tensor)` sums it onto rank 0 in place (default: torch.distributed.reduce); `resolve(sum)` runs on
-    rank 0 only.  Returns (image on rank 0 | None, sum tensor)."""
+    rank 0 only.  `reduce_events`: optional (begin, end) torch.cuda.Event pair recorded on the current stream around
+    the collective.  Returns (image on rank 0 | None, sum tensor)."""
     begin, end = shard_range(samples, rank, world)
     total = render_shard(begin, end - begin)
     if world > 1:
+        if reduce_events:
+            reduce_events[0].record()
         if reduce_fn is None:
             import torch.distributed as dist
             dist.reduce(total, dst=0, op=dist.ReduceOp.SUM)
         else:
             reduce_fn(total)
+        if reduce_events:
+            reduce_events[1].record()
     if rank == 0:
         return resolve(total), total
     return None, total
-
-
-def stream_scope(renderer_obj):
-    """Context manager that makes `renderer_obj.stream` torch's current stream (a no-op for CPU stand-ins)."""
-    import contextlib
-    st = getattr(renderer_obj, "stream", None)
-    if st is None:
-        return contextlib.nullcontext()
-    import torch
-    return torch.cuda.stream(st)
 
 
 class GpuShardRenderer:
@@ -94,7 +90,7 @@ class GpuShardRenderer:
             out = d_rgb.cpu()          # same stream: ordered after the resolve kernel, synchronises it
         return out.numpy().reshape(self.shape)
 
-    def render(self, samples: int, rank: int, world: int):
+    def render(self, samples: int, rank: int, world: int, reduce_events=None):
         """One sharded render step: (image on rank 0 | None, this rank's / the reduced sum tensor)."""
         with self.use_stream():    # dist.reduce orders itself against torch's CURRENT stream
-            return render_sharded(self.render_shard, self.resolve, samples, rank, world)
+            return render_sharded(self.render_shard, self.resolve, samples, rank, world, reduce_events=reduce_events)
