@@ -44,7 +44,7 @@ EXPORTS = [
     "fw_env_sample", "fw_texture_sample", "fw_material_texture", "fw_camera", "fw_last_error", "fw_version",
     "fw_device_count", "fw_measure_peaks", "fw_selftest_shared_division", "fw_obj_load", "fw_obj_num_models",
     "fw_obj_model_name", "fw_obj_model_sizes", "fw_obj_model_copy", "fw_obj_destroy", "fw_hdr_load", "fw_hdr_free", "fw_set_profiling", "fw_set_batch_paths", "fw_release_cached_memory",
-    "fw_resolve_host", "fw_render_multi",
+    "fw_resolve_host", "fw_render_multi", "fw_scene_walk_info",
 ]
 
 _lib = None
@@ -104,6 +104,7 @@ def lib():
         L.fw_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.fw_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.fw_set_batch_paths.argtypes = [C.c_void_p, C.c_uint64]
+        L.fw_scene_walk_info.argtypes = [C.c_void_p, C.c_void_p]
         L.fw_resolve_host.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p]
         L.fw_render_multi.argtypes = [C.c_void_p, C.POINTER(FwParams), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                       C.POINTER(FwStats), C.POINTER(C.c_double)]

@@ -108,14 +108,21 @@ static int upload(fw_scene* sc, const std::vector<T>& host, const T** dev) {
 static void free_path_state(PathState& ps) {
     auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     for (int i = 0; i < 2; ++i) { fr(ps.xo[i]); fr(ps.xd[i]); }
-    for (HitQueue& q : ps.hq) { fr(q.o); fr(q.d); fr(q.w); fr(q.b); }
+    for (HitQueue& q : ps.hq) { fr(q.o); fr(q.d); fr(q.w); }
     fr(ps.atten); fr(ps.radiance); fr(ps.counters);
+}
+static void free_walk(RenderCtx* c) {
+    if (c->walk.tkey) cudaFree(c->walk.tkey);
+    if (c->walk.entries) cudaFree(c->walk.entries);
+    c->walk = WalkAuxHost{};
+    c->walk_key_cap = c->walk_ent_total = 0;
 }
 static void destroy_ctx(RenderCtx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     free_path_state(c->ps);
+    free_walk(c);
     if (c->arena) cudaFree(c->arena);
     for (void* p : c->arena_retired) cudaFree(p);
     for (auto& t : c->tex_cache) { if (t.tex) cudaDestroyTextureObject(t.tex); if (t.arr) cudaFreeArray(t.arr); }
@@ -400,7 +407,7 @@ static int commit_uploads(fw_scene* sc) {
     int rc;
 #define UP(field) if ((rc = upload(sc, F.field, &D.field)) != FW_OK) return rc
     UP(nodes); UP(top_items); UP(leaf_posr); UP(leaf_meta); UP(obj_posr); UP(obj_meta); UP(obj_rot); UP(obj_irot); UP(shapes); UP(meshes);
-    UP(tri_verts); UP(tri_normals); UP(tri_uvs); UP(mats); UP(texs);
+    UP(tri_verts); UP(tri_perm); UP(tri_normals); UP(tri_uvs); UP(mats); UP(texs);
 #undef UP
     std::vector<ImageRec> images(std::max<size_t>(sc->desc.assets.size(), 1));
     memset(images.data(), 0, images.size() * sizeof(ImageRec));
@@ -430,6 +437,7 @@ static int commit_uploads(fw_scene* sc) {
     if ((rc = upload(sc, images, &D.images)) != FW_OK) return rc;
     D.n_objects = (int)sc->desc.objects.size();
     D.n_nodes = (int)(F.nodes.size() / 8);
+    D.n_tris = (int)(F.tri_verts.size() / 3);
     {
         int rc_bits = F.top_root_code;
         float rcf;
@@ -442,6 +450,7 @@ static int commit_uploads(fw_scene* sc) {
     D.has_unbounded = F.has_unbounded ? 1 : 0;
     D.nan_bvh_obj = F.nan_bvh_obj; D.nan_bvh_prim = F.nan_bvh_prim;
     D.nan_lin_obj = F.nan_lin_obj; D.nan_lin_prim = F.nan_lin_prim;
+    for (int k = 0; k < FW_MAX_WALK_MESHES; ++k) D.mesh_rank[k] = F.mesh_rank[k];
     for (const MatRec& m : F.mats) sc->mat_present[m.kind] = true;
     {
         // render.rs:31 with a black ColorEnv: an escaping path returns attenuation-chain * 0.  That is exactly 0
@@ -465,6 +474,8 @@ static int commit_uploads(fw_scene* sc) {
     if (sc->lin_prog_ok) memcpy(sc->lin_prog.w, F.lin_words.data(), F.lin_words.size() * sizeof(float4));
     sc->plan.has_mesh = F.has_mesh; sc->plan.has_top_mesh = F.has_top_mesh; sc->plan.has_medium_mesh = F.has_medium_mesh;
     sc->plan.lin_prog_ok = sc->lin_prog_ok; sc->plan.lin_generic = F.lin_generic; sc->plan.lin_rect_tests = F.lin_rect_tests;
+    sc->plan.walk = F.walk_ok && F.has_top_mesh;   // mesh walk kernels (sphere-only trees stay on the lock-step kernel)
+    if (const char* e = getenv("FW_WALK")) sc->plan.walk = sc->plan.walk && atoi(e) != 0;
     // uploads ran on the context's stream; renders may be issued on another one (fw_render_accumulate_device)
     FW_CUDA(cudaStreamSynchronize(sc->ctx->stream));
     sc->committed = true;
@@ -513,6 +524,13 @@ int fw_scene_linear_program(const fw_scene* sc, float* out, int cap) {
     int n = (int)sc->flat.lin_words.size();
     if (out) memcpy(out, sc->flat.lin_words.data(), sizeof(float4) * (size_t)std::max(0, std::min(n, cap)));
     return n;
+}
+int fw_scene_walk_info(const fw_scene* sc, int out[6]) {
+    if (!sc || !sc->built || !out) return set_error(FW_ERR_STATE, "scene not built (fw_scene_build_host / fw_scene_commit)");
+    const HostFlat& F = sc->flat;
+    out[0] = F.walk_ok ? 1 : 0; out[1] = F.n_top_meshes; out[2] = F.top_wide_depth; out[3] = F.mesh_wide_depth;
+    out[4] = F.walk_prim_bits; out[5] = (int)(F.tri_verts.size() / 3);
+    return FW_OK;
 }
 int fw_material_texture(const fw_scene* sc, int material) {
     if (!sc || material < 0 || material >= (int)sc->desc.mats.size()) return -1;
@@ -578,6 +596,7 @@ static int ensure_path_state(fw_scene* sc, size_t cap) {
     PathState& ps = ctx->ps;
     if (ctx->ps_cap < cap || ctx->ps_nseg_max < nseg_max) {
         free_path_state(ps);
+        free_walk(ctx);
         ctx->ps_cap = 0;
     }
     cap = std::max(cap, ctx->ps_cap);   // streams added later for another scene get the context's full size
@@ -593,17 +612,35 @@ static int ensure_path_state(fw_scene* sc, size_t cap) {
     for (int i = 0; i < 2; ++i) { NEED(ps.xo[i], qcap); NEED(ps.xd[i], qcap); }
     NEED(ps.atten, cap * FW_MAX_DEPTH);
     NEED(ps.radiance, cap);
-    const bool mesh = sc->flat.has_mesh;
-    for (int k = 0; k < FW_NUM_QUEUES; ++k) {
-        bool used = k == MAT_MISS || (k < MAT_NUM_QUEUES && sc->mat_present[k]) || (k == FW_Q_MESH && sc->flat.has_top_mesh);
+    for (int k = 0; k < 8; ++k) {   // ps.hq[]
+        bool used = k == MAT_MISS || (k < MAT_NUM_QUEUES && sc->mat_present[k]) ||
+                    (k == FW_Q_MESH && sc->flat.has_top_mesh);   // rays that enter a mesh (two-pass extend / mesh walk)
         if (!used) continue;
         NEED(ps.hq[k].d, qcap);
         if (k == MAT_MISS) continue;
         NEED(ps.hq[k].o, qcap);
         NEED(ps.hq[k].w, qcap);
-        if (mesh) NEED(ps.hq[k].b, qcap);
     }
 #undef NEED
+    if (sc->plan.walk && sc->flat.has_top_mesh) {
+        // walk kernels on a scene with top-level meshes: one 64-bit key per queue slot, and an entry queue with room for
+        // every (ray, mesh) combination of a segment (n_top_meshes <= 8 is part of walk_ok)
+        const size_t ent_per_seg_max = (size_t)sc->flat.n_top_meshes;
+        const size_t ent_total = qcap * ent_per_seg_max;
+        if (ctx->walk_key_cap < qcap) {
+            if (ctx->walk.tkey) cudaFree(ctx->walk.tkey);
+            ctx->walk.tkey = nullptr; ctx->walk_key_cap = 0;
+            FW_CUDA(cudaMalloc(&ctx->walk.tkey, qcap * sizeof(unsigned long long)));
+            ctx->walk_key_cap = qcap;
+        }
+        if (ctx->walk_ent_total < ent_total) {
+            if (ctx->walk.entries) cudaFree(ctx->walk.entries);
+            ctx->walk.entries = nullptr; ctx->walk_ent_total = 0;
+            FW_CUDA(cudaMalloc(&ctx->walk.entries, ent_total * 8));
+            ctx->walk_ent_total = ent_total;
+        }
+    }
+    ctx->walk.prim_bits = sc->flat.walk_prim_bits;
     if (!ps.counters) FW_CUDA(cudaMalloc(&ps.counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * nseg_max));
     ps.cap = (uint32_t)cap;
     ctx->ps_cap = cap;
@@ -708,8 +745,20 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
     const size_t counter_bytes = sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * (size_t)ps.nseg;
     FW_CUDA(cudaMemsetAsync(ps.counters, 0, counter_bytes, st));
     unsigned sm = (unsigned)sc->sm_count;
+    // FW_DEBUG_SYNC=1: synchronise after every stage and name the one that faulted (debugging aid; slow)
+    static const bool debug_sync = getenv("FW_DEBUG_SYNC") != nullptr;
+    auto stage = [&](const char* what, uint32_t bounce) -> int {
+        if (!debug_sync) return FW_OK;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return set_error(FW_ERR_CUDA, std::string(what) + " (bounce " + std::to_string(bounce) + "): " + cudaGetErrorString(e));
+        return FW_OK;
+    };
+#define FW_STAGE(what, bounce) do { int rc__ = stage(what, bounce); if (rc__ != FW_OK) return rc__; } while (0)
     launch_raygen(cam, b, seed, ps, st);
     tot.launches++;
+    FW_STAGE("raygen", 0);
     for (uint32_t bounce = 0; bounce <= (uint32_t)FW_MAX_DEPTH; ++bounce) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (sc->profiling) {
@@ -722,26 +771,44 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
             if (rc != FW_OK) return rc;
             tot.launches++;
         } else {
-            tot.launches += launch_extend(sc->plan, use_bvh, sc->lin_prog, S, ps, b, seed, bounce, st);
+            if (use_bvh && sc->plan.walk && sc->plan.two_pass) {
+                WalkAuxHost ax = sc->ctx->walk;
+                ax.ent_cap = ps.seg_cap * (uint32_t)std::max(1, sc->flat.n_top_meshes);
+                if (debug_sync) {
+                    for (int part = 0; part < 3; ++part) {
+                        launch_extend_walk_part(part, sc->plan, S, ps, b, seed, bounce, ax, st);
+                        FW_STAGE(part == 0 ? "extend pass 1 (entries)" : part == 1 ? "mesh walk" : "mesh classify", bounce);
+                    }
+                    tot.launches += 3;
+                } else {
+                    tot.launches += launch_extend_walk(sc->plan, S, ps, b, seed, bounce, ax, st);
+                }
+            } else {
+                tot.launches += launch_extend(sc->plan, use_bvh, sc->lin_prog, S, ps, b, seed, bounce, st);
+            }
         }
         if (sc->profiling) {
             FW_CUDA(cudaEventRecord(e1, st));
             tot.extend_events.emplace_back(e0, e1);
         }
         tot.extend_launches++;
+        FW_STAGE("extend", bounce);
         if (!sc->miss_is_zero) {
             launch_miss(S, ps, bounce, st);
             tot.launches++;
+            FW_STAGE("miss", bounce);
         }
         if (sc->mat_present[MAT_EMISSIVE]) {
             launch_shade_emissive(S, ps, bounce, st);
             tot.launches++;
+            FW_STAGE("shade emissive", bounce);
         }
         if (bounce < (uint32_t)FW_MAX_DEPTH) {
             for (int mat : {MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_ISOTROPIC})
                 if (sc->mat_present[mat]) {
                     launch_shade_scatter(mat, S, ps, b, seed, bounce, st);
                     tot.launches++;
+                    FW_STAGE(mat == MAT_LAMBERTIAN ? "shade lambertian" : mat == MAT_METAL ? "shade metal" : mat == MAT_DIELECTRIC ? "shade dielectric" : "shade isotropic", bounce);
                 }
         }
     }
@@ -749,6 +816,8 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
     tot.launches++;
     launch_tally(ps, sc->ctx->d_rays, st);
     tot.launches++;
+    FW_STAGE("accumulate / tally", 0);
+#undef FW_STAGE
     FW_CUDA(cudaGetLastError());
     return FW_OK;
 }

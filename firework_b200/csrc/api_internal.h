@@ -38,6 +38,8 @@ struct RenderCtx {
     PathState ps{};
     size_t ps_cap = 0;
     size_t ps_nseg_max = 0;
+    WalkAuxHost walk{};          // key / entry buffers of the walk kernels (sized with the path state)
+    size_t walk_key_cap = 0, walk_ent_total = 0;
     cudaStream_t stream = nullptr;
     float* d_sum = nullptr;
     unsigned char* d_rgb = nullptr;

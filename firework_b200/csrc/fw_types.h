@@ -55,6 +55,8 @@ struct LinProgram {
 constexpr int OBJ_KIND_MASK = 0xff;
 constexpr int OBJ_ROTATED = 1 << 8;   // cos_trace < 0.999 (scene.rs:242-246): ray is rotated into object space
 constexpr int OBJ_FLIP = 1 << 9;      // RenderObject.flip_normals (scene.rs:259-261)
+constexpr int OBJ_MESH_ORD_SHIFT = 16; // bits 16..20: ordinal of a top-level TriangleMesh object among the scene's meshes (0..7; walk kernels)
+constexpr int FW_MAX_WALK_MESHES = 8;  // top-level meshes a scene may have for the mesh-entry path (else: lock-step pass 2)
 
 struct ShapeRec {  // 48 B
     int kind, material, i0, i1;
@@ -114,6 +116,8 @@ struct DeviceScene {
     const ShapeRec* shapes;
     const MeshRec* meshes;
     const float4* tri_verts;   // per triangle slot: 3 x float4 (p0, p1, p2; p0.w = asfloat(original index))
+    const float4* tri_perm;    // 3 copies of tri_verts, copy kz holds every vertex as (v[kx], v[ky], v[kz]) for the dominant
+                               // axis kz of mesh.rs:146-153 (kx = kz+1, ky = kx+1 mod 3): [(kz * n_tris + slot) * 3 + vertex]
     const float4* tri_normals; // per triangle slot: 3 x float4 (only for meshes with normals; else unused)
     const float2* tri_uvs;     // per triangle slot: 3 x float2 (default (0,0),(1,0),(0,1) if the mesh has none)
     const MatRec* mats;
@@ -122,12 +126,14 @@ struct DeviceScene {
     EnvRec env;
     int n_objects;
     int n_nodes;
+    int n_tris;                // triangle slots of all meshes (stride of tri_perm's copies)
     int top_root_is_valid;     // 0 if the top-level BVH was not built (linear scenes may still build it)
     int has_medium;
     int has_unbounded;         // some top-level item's box does not bound its geometry (Disk): node flags matter
     // Closest-hit answer for a ray whose direction is NaN in all three components (see nan_direction_winner):
     // object id (-1 = miss) and primitive (mesh: last triangle slot, Rect3d: last face), for BVH and linear roots.
     int nan_bvh_obj, nan_bvh_prim, nan_lin_obj, nan_lin_prim;
+    int mesh_rank[FW_MAX_WALK_MESHES];   // top-level DFS rank of the mesh object with ordinal k (scenes with <= 8 top-level meshes)
 };
 
 struct CameraRec {  // camera.rs:7-16

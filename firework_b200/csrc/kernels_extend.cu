@@ -1,6 +1,6 @@
 // Extend kernels: closest hit for every queued ray (render.rs:19 -> bvh.rs:115-151 / scene.rs:137-149).
 #include "launch.h"
-#include "wavefront.cuh"
+#include "walk.cuh"
 
 namespace fw {
 
@@ -22,11 +22,29 @@ __global__ void __launch_bounds__(FW_BLOCK) extend_bvh_debug_kernel(DeviceScene 
 // against the non-mesh objects and the mesh root boxes; rays that must enter a mesh are compacted into the mesh
 // queue (with the pass-1 winner and its rank) and finished by pass 2, where every lane of a warp is doing real
 // mesh traversal.
-template <bool NESTED>
+// ENTRIES: the mesh walk (kernels_walk.cu) finishes the bounce instead of pass 2: every ray that must enter a mesh also
+// gets its pass-1 winner written as a 64-bit key (walk.cuh pack_key) and one (mesh-queue slot, mesh rank) entry per mesh
+// root box it hit.
+template <bool NESTED, bool ENTRIES>
 __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass1_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
-                                                                                uint32_t bounce) {
-    FW_EXTEND_PROLOGUE(FW_NUM_QUEUES)
+                                                                                uint32_t bounce, WalkAux aux) {
+    __shared__ uint32_t s_fill[FW_NUM_QUEUES];
+    const uint32_t seg = blockIdx.x;
+    const uint32_t in_count = counter_row(ps, bounce, FW_Q_EXTEND)[seg];
+    seg_open<FW_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), seg);
+    const uint32_t seg_base = seg * ps.seg_cap;
+    for (uint32_t e0 = 0; e0 < in_count; e0 += FW_BLOCK) {
+        const bool valid = e0 + threadIdx.x < in_count;
+        uint32_t path = 0, pending = 0u;
+        float3 o = f3(1e30f, 1e30f, 1e30f), d = f3(1.0f, 1.0f, 1.0f);
+        Winner w;
+        w.found = false; w.t = 0.0f; w.obj = -1; w.rank = -1; w.h.t = 0.0f; w.h.prim = 0;
+        w.h.b0 = w.h.b1 = w.h.b2 = 0.0f;
+        int mine = -1, material = -1;
         if (valid) {
+            const size_t slot_in = (size_t)seg_base + e0 + threadIdx.x;
+            float4 ro = ld_stream(&ps.xo[bounce & 1][slot_in]), rd = ld_stream(&ps.xd[bounce & 1][slot_in]);
+            o = f3(ro); d = f3(rd); path = __float_as_uint(ro.w);
             RngKey key{seed, 0u, 0u, bounce};
             batch_path(b, path, key.pixel, key.sample);
             UnifiedWalker<false, NESTED, true, 1> wk;
@@ -37,9 +55,24 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass1_k
                 }
             }
             w = wk.w;
-            if (wk.pending) mine = FW_Q_MESH;   // queue 6 is never selected (its counter slot belongs to the shade kernels)
+            pending = wk.pending;
+            if (pending) mine = FW_Q_MESH;
+            else mine = classify_winner(S, w, material);
         }
-    FW_EXTEND_EPILOGUE(FW_NUM_QUEUES)
+        const uint32_t slot = enqueue_hit<FW_Q_MESH + 1>(ps, s_fill, seg_base, mine, o, d, path, w, material);
+        if (ENTRIES && pending) {
+            aux.tkey[slot] = w.found ? pack_key(w.t, w.rank, w.h.prim, aux.prim_bits) : FW_KEY_NONE;
+            uint32_t m = pending;
+            while (m) {
+                const int ord = __ffs(m) - 1;
+                m &= m - 1u;
+                const uint32_t e = atomicAdd(&s_fill[FW_Q_ENTRY], 1u);
+                FW_WALK_CHECK(e < aux.ent_cap && ord < FW_MAX_WALK_MESHES, "entry overflow e=%u cap=%u ord=%d\n", e, aux.ent_cap, ord);
+                aux.entries[(size_t)seg * aux.ent_cap + e] = make_uint2(slot - seg_base, (uint32_t)S.mesh_rank[ord]);
+            }
+        }
+    }
+    seg_close<FW_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), seg);
 }
 template <bool NESTED>
 __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass2_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
@@ -121,11 +154,12 @@ int launch_extend(const ExtendPlan& plan, bool use_bvh, const LinProgram& P, con
                   const Batch& b, uint2 seed, uint32_t bounce, cudaStream_t st) {
     const unsigned G = ps.nseg;   // one block per segment
     if (use_bvh && plan.has_top_mesh && plan.two_pass) {
+        WalkAux none{};
         if (plan.has_medium_mesh) {
-            extend_pass1_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+            extend_pass1_kernel<true, false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, none);
             extend_pass2_kernel<true><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
         } else {
-            extend_pass1_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
+            extend_pass1_kernel<false, false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, none);
             extend_pass2_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
         }
         return 2;
@@ -156,6 +190,13 @@ int launch_extend(const ExtendPlan& plan, bool use_bvh, const LinProgram& P, con
         extend_linear_kernel<false><<<G, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce);
     }
     return 1;
+}
+void launch_extend_pass1_entries(bool nested, const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce,
+                                 const WalkAuxHost& ax, cudaStream_t st) {
+    WalkAux aux;
+    aux.tkey = ax.tkey; aux.entries = reinterpret_cast<uint2*>(ax.entries); aux.ent_cap = ax.ent_cap; aux.prim_bits = ax.prim_bits;
+    if (nested) extend_pass1_kernel<true, true><<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, aux);
+    else extend_pass1_kernel<false, true><<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, aux);
 }
 void launch_extend_debug(const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce, uint32_t* steps,
                          cudaStream_t st) {

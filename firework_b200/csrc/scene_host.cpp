@@ -837,6 +837,7 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
 
     size_t nobj = desc.objects.size();
     out.obj_aabb.resize(nobj);
+    int mesh_ordinal = 0;
     for (size_t i = 0; i < nobj; ++i) {
         const ObjectDesc& o = desc.objects[i];
         const ShapeRec& s = desc.shapes[o.shape];
@@ -866,6 +867,10 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         out.obj_aabb[i] = Box{V3{rb.mn.x + o.position.x, rb.mn.y + o.position.y, rb.mn.z + o.position.z},
                               V3{rb.mx.x + o.position.x, rb.mx.y + o.position.y, rb.mx.z + o.position.z}};
         int flags = s.kind | (rotated ? OBJ_ROTATED : 0) | (o.flip_normals ? OBJ_FLIP : 0);
+        if (s.kind == SH_MESH) {   // ordinal among the top-level meshes (scene order); only meaningful when there are <= 8
+            flags |= (mesh_ordinal & (FW_MAX_WALK_MESHES - 1)) << OBJ_MESH_ORD_SHIFT;
+            ++mesh_ordinal;
+        }
         out.obj_posr.push_back(float4{o.position.x, o.position.y, o.position.z, s.kind == SH_SPHERE ? s.f[0] : 0.0f});
         out.obj_meta.push_back(int4{flags, s.material, o.shape, 0});
         for (int c = 0; c < 3; ++c) {
@@ -952,6 +957,21 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         W.push_back(float4{0, as_float(LIN_END), 0, 0});
     }
 
+    // Triangle vertices pre-permuted for the three possible dominant axes of a ray (mesh.rs:146-153 permutes every vertex
+    // per test: nine selects the mesh walk's test phase does not have to execute; same values, so the same bits).
+    {
+        const size_t nt = out.tri_verts.size() / 3;
+        out.tri_perm.resize(out.tri_verts.size() * 3);
+        for (int kz = 0; kz < 3; ++kz) {
+            const int kx = (kz + 1) % 3, ky = (kx + 1) % 3;
+            for (size_t i = 0; i < nt * 3; ++i) {
+                const float4& v = out.tri_verts[i];
+                const float c[3] = {v.x, v.y, v.z};
+                out.tri_perm[(size_t)kz * nt * 3 + i] = float4{c[kx], c[ky], c[kz], v.w};
+            }
+        }
+    }
+
     // top-level BVH (bvh.rs:79-98), always built: linear-scan renders simply do not use it
     FlatBVH top;
     if (!build_bvh(out.obj_aabb, top, err, &obj_unbounded)) return false;
@@ -982,11 +1002,16 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
                 max_prim = std::max(max_prim, sh.i1 - 1);
             }
         }
+        if (out.n_top_meshes <= FW_MAX_WALK_MESHES)
+            for (size_t rank = 0; rank < top.items.size(); ++rank) {
+                const int4& m = out.obj_meta[top.items[rank]];
+                if ((m.x & OBJ_KIND_MASK) == SH_MESH) out.mesh_rank[(m.x >> OBJ_MESH_ORD_SHIFT) & (FW_MAX_WALK_MESHES - 1)] = (int)rank;
+            }
         int rank_bits = 1;
         while (rank_bits < 31 && ((size_t)1 << rank_bits) < desc.objects.size()) ++rank_bits;
         out.walk_prim_bits = 32 - rank_bits;
         const bool key_fits = (size_t)max_prim < ((size_t)1 << out.walk_prim_bits) && ((size_t)1 << rank_bits) >= desc.objects.size();
-        out.walk_ok = roots_wide && key_fits && out.n_top_meshes <= 8 && 3 * top.wide_depth + 4 <= 64 &&
+        out.walk_ok = roots_wide && key_fits && out.n_top_meshes >= 1 && out.n_top_meshes <= FW_MAX_WALK_MESHES && 3 * top.wide_depth + 4 <= 64 &&
                       3 * max_mesh_wide_depth + 4 <= 64;
     }
     out.top_depth = top.max_depth;

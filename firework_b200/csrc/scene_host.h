@@ -83,7 +83,7 @@ struct HostFlat {
     std::vector<Box> obj_aabb;  // world boxes (scene.rs:167-212), kept for tests / stats
     std::vector<ShapeRec> shapes;
     std::vector<MeshRec> meshes;
-    std::vector<float4> tri_verts, tri_normals;
+    std::vector<float4> tri_verts, tri_normals, tri_perm;
     std::vector<float2> tri_uvs;
     std::vector<MatRec> mats;
     std::vector<TexRec> texs;
@@ -101,6 +101,7 @@ struct HostFlat {
     // scene has few enough top-level meshes for the entry queue, and (t, rank, primitive) packs into one 64-bit key.
     int top_wide_depth = 0, mesh_wide_depth = 0;
     int n_top_meshes = 0;           // render objects that ARE a TriangleMesh
+    int mesh_rank[FW_MAX_WALK_MESHES] = {0, 0, 0, 0, 0, 0, 0, 0};   // DFS rank of the mesh object with ordinal k
     int walk_prim_bits = 0;         // key = t bits << 32 | ~rank << prim_bits | ~prim
     bool walk_ok = false;
 };

@@ -23,6 +23,8 @@
 // global memory; classify_kernel then sorts the rays into the shade queues.  The barycentrics of the winning triangle
 // are recomputed by finalize_hit (same arithmetic, once per ray) instead of travelling through the queues.
 #pragma once
+#include <cstdio>
+
 #include "wavefront.cuh"
 
 namespace fw {
@@ -33,6 +35,10 @@ namespace fw {
 #ifndef FW_WALK_REFILL_IDLE
 #define FW_WALK_REFILL_IDLE 12    // refill a warp when at least this many of its lanes have no node left to visit
 #endif
+#ifndef FW_WALK_CHECKS
+#define FW_WALK_CHECKS 0          // 1 = bounds checks with printf + trap in the walk kernels (debug builds)
+#endif
+#define FW_WALK_CHECK(cond, ...) do { if (FW_WALK_CHECKS && !(cond)) { printf(__VA_ARGS__); __trap(); } } while (0)
 constexpr int FW_WALK_STACK = 64;      // deferred interior children per lane (3 per wide level; checked at flatten)
 constexpr int FW_WALK_PAIRS = 160;     // < 32 left over + at most 4 new per lane
 constexpr int FW_WALK_WARPS = FW_BLOCK / 32;
@@ -67,25 +73,69 @@ struct WalkAux {
     int prim_bits;
 };
 
-// One wide-node visit for the walk loop.  Children that survive the slab test and the distance cull are split into
-// leaves (returned in l0..l3 for the caller to emit) and interior nodes (nearest becomes `node`, the rest are pushed).
-FW_DEV void walk_visit(const float4* __restrict__ nodes, int& node, float3 o, float3 inv, float bound, int* stk_code,
-                       float* stk_te, int& sp, bool& l0, bool& l1, bool& l2, bool& l3, int4& cc) {
+// ---- culling that can not change the winner ---------------------------------------------------------------------
+// FW_WALK_CULL selects the distance a child box is culled (and ordered) by against the best hit so far:
+//   1  the box-entry parameter of the slab test (what the lock-step kernels use).  Fast, but only ALMOST safe: a triangle
+//      seen nearly edge-on is accepted with barycentrics that are rounding noise, and its t = sum(b_i z_i) (mesh.rs:188-196)
+//      can then land anywhere inside the triangle's depth range along the ray's axis kz — below the entry parameter of
+//      its own leaf box.  Such a hit is lost if an unrelated hit culled the leaf first (measured: ~3e-8 of the rays on
+//      suzanne, and WHICH is lost depends on scheduling once warps fetch work dynamically);
+//   2  the entry parameter of the kz-axis slab alone, (near_z - o_z) * (1 / d_z), kz = the axis Triangle::hit permutes to z
+//      (mesh.rs:146-153).  Every accepted hit satisfies t >= min_i z_i up to a few ulp, z_i = (p_i.z - o.z) * (1 / d.z) being
+//      computed from a vertex inside the box with the same subtraction, the same reciprocal and monotonic rounding, so
+//      t >= that slab entry: a box skipped because the entry exceeds best_t + margin can not hold the winner.  The set of
+//      boxes skipped then depends on timing, the winner does not — results are the reference's exhaustive traversal
+//      (bvh.rs:134-146), bit for bit and run to run;
+//   0  no hit-dependent culling inside an entry (reference traversal order of magnitude; for measurements).
+// The slab test itself is axis-order independent (max / min of the same six products), so the walker keeps the ray
+// permuted to (kx, ky, kz) and loads the node rows in that order; the kz product comes out of the test for free.
+#ifndef FW_WALK_CULL
+#define FW_WALK_CULL 2
+#endif
+
+// Row byte offsets inside a wide node for a ray whose axes are permuted to (kx, ky, kz): near / far plane rows of each
+// permuted axis, one byte each (near plane = max row where the direction is negative, see wide_visit).
+FW_DEV void walk_rows(int kz, float3 inv_perm, uint32_t& near_pack, uint32_t& far_pack) {
+    const int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
+    const uint32_t s0 = inv_perm.x < 0.0f ? 48u : 0u, s1 = inv_perm.y < 0.0f ? 48u : 0u, s2 = inv_perm.z < 0.0f ? 48u : 0u;
+    near_pack = (16u * kx + s0) | ((16u * ky + s1) << 8) | ((16u * kz + s2) << 16);
+    far_pack = (16u * kx + 48u - s0) | ((16u * ky + 48u - s1) << 8) | ((16u * kz + 48u - s2) << 16);
+}
+
+// One wide-node visit for the walk loop; o / inv are the ray permuted to (kx, ky, kz).  Children that survive the slab test
+// (aabb.rs:30-50 arithmetic) and the cull are split into leaves (returned in l0..l3 for the caller to emit) and interior
+// nodes (nearest becomes `node`, the rest are pushed with their cull distance).
+FW_DEV void walk_visit(const float4* __restrict__ nodes, int& node, float3 o, float3 inv, uint32_t near_pack, uint32_t far_pack,
+                       float bound, int* stk_code, float* stk_te, int& sp, bool& l0, bool& l1, bool& l2, bool& l3, int4& cc) {
     const float tmin = 0.001f, tmax = 2e9f;   // render.rs:19
     const float4* n = &nodes[8 * node];
-    const unsigned sx = inv.x < 0.0f ? 48u : 0u, sy = inv.y < 0.0f ? 48u : 0u, sz = inv.z < 0.0f ? 48u : 0u;
-    const uintptr_t nb = reinterpret_cast<uintptr_t>(n);
-    auto row = [nb](unsigned byte_off) { return reinterpret_cast<const float4*>(nb | (uintptr_t)byte_off); };
-    float4 nx = __ldg(row(sx)), ny = __ldg(row(16u + sy)), nz = __ldg(row(32u + sz));
-    float4 fx = __ldg(row(48u - sx)), fy = __ldg(row(64u - sy)), fz = __ldg(row(80u - sz));
+    const uintptr_t nb = reinterpret_cast<uintptr_t>(n);   // 128-byte aligned: row offsets are OR-ed in
+    auto row = [nb](uint32_t byte_off) { return reinterpret_cast<const float4*>(nb | (uintptr_t)byte_off); };
+    const float4 nx = __ldg(row(near_pack & 0xffu)), ny = __ldg(row((near_pack >> 8) & 0xffu)), nz = __ldg(row(near_pack >> 16));
+    const float4 fx = __ldg(row(far_pack & 0xffu)), fy = __ldg(row((far_pack >> 8) & 0xffu)), fz = __ldg(row(far_pack >> 16));
     cc = __ldg(reinterpret_cast<const int4*>(n + 6));
-    float t0, t1, t2, t3;
-    bool h0 = slab_near_far(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, o, inv, tmin, tmax, t0);
-    bool h1 = slab_near_far(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, o, inv, tmin, tmax, t1);
-    bool h2 = slab_near_far(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, o, inv, tmin, tmax, t2);
-    bool h3 = slab_near_far(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, o, inv, tmin, tmax, t3);
+    float e0, e1, e2, e3;   // box entry (all three slabs)
+    float z0, z1, z2, z3;   // entry of the kz slab alone
+    auto slab = [&](float cnx, float cny, float cnz, float cfx, float cfy, float cfz, float& te, float& tz) {
+        tz = (cnz - o.z) * inv.z;
+        float lo = fmaxf(fmaxf(fmaxf(tmin, (cnx - o.x) * inv.x), (cny - o.y) * inv.y), tz);
+        float hi = fminf(fminf(fminf(tmax, (cfx - o.x) * inv.x), (cfy - o.y) * inv.y), (cfz - o.z) * inv.z);
+        te = lo;
+        return hi > lo;
+    };
+    bool h0 = slab(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, e0, z0);
+    bool h1 = slab(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, e1, z1);
+    bool h2 = slab(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, e2, z2);
+    bool h3 = slab(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, e3, z3);
+    // cull / order distance (a NaN product, 0 * inf, must not drop the child: fmaxf returns the other operand)
+    float t0 = FW_WALK_CULL == 2 ? fmaxf(z0, -FW_FLT_MAX) : e0, t1 = FW_WALK_CULL == 2 ? fmaxf(z1, -FW_FLT_MAX) : e1;
+    float t2 = FW_WALK_CULL == 2 ? fmaxf(z2, -FW_FLT_MAX) : e2, t3 = FW_WALK_CULL == 2 ? fmaxf(z3, -FW_FLT_MAX) : e3;
     h0 = h0 && !(t0 > bound); h1 = h1 && !(t1 > bound); h2 = h2 && !(t2 > bound); h3 = h3 && !(t3 > bound);
-    l0 = h0 && cc.x < 0; l1 = h1 && cc.y < 0; l2 = h2 && cc.z < 0; l3 = h3 && cc.w < 0;   // empty slots never pass the slab test
+    // leaf children; empty slots (code FW_CODE_EXIT, inverted box) are excluded explicitly: a direction with NaN / infinite
+    // components (scatter off a near-zero interpolated normal) passes EVERY slab test, f32::max / min ignoring NaN
+    const int none = FW_CODE_EXIT;
+    l0 = h0 && cc.x < 0 && cc.x != none; l1 = h1 && cc.y < 0 && cc.y != none;
+    l2 = h2 && cc.z < 0 && cc.z != none; l3 = h3 && cc.w < 0 && cc.w != none;
     const float miss = __int_as_float(0x7f800000);
     t0 = (h0 && cc.x >= 0) ? t0 : miss; t1 = (h1 && cc.y >= 0) ? t1 : miss;
     t2 = (h2 && cc.z >= 0) ? t2 : miss; t3 = (h3 && cc.w >= 0) ? t3 : miss;
@@ -93,6 +143,7 @@ FW_DEV void walk_visit(const float4* __restrict__ nodes, int& node, float3 o, fl
     cswap(t0, c0, t1, c1);
     cswap(t2, c2, t3, c3);
     cswap(t0, c0, t2, c2);   // (t0, c0) = nearest surviving interior child
+    FW_WALK_CHECK(sp + 3 <= FW_WALK_STACK, "walk stack overflow sp=%d node=%d\n", sp, node);
     if (t3 < miss) { stk_code[sp] = c3; stk_te[sp] = t3; ++sp; }
     if (t2 < miss) { stk_code[sp] = c2; stk_te[sp] = t2; ++sp; }
     if (t1 < miss) { stk_code[sp] = c1; stk_te[sp] = t1; ++sp; }
@@ -106,6 +157,7 @@ FW_DEV int walk_emit(WalkWarp& W, int npairs, bool l0, bool l1, bool l2, bool l3
     const int c = (int)l0 + (int)l1 + (int)l2 + (int)l3;
     const unsigned b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2), b2 = __ballot_sync(0xffffffffu, c & 4);
     if ((b0 | b1 | b2) == 0u) return npairs;
+    FW_WALK_CHECK(npairs + __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) <= FW_WALK_PAIRS, "pair buffer overflow %d\n", npairs);
     int off = npairs + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
     if (l0) W.pairs[off++] = ((uint32_t)(~cc.x) << 5) | lane;
     if (l1) W.pairs[off++] = ((uint32_t)(~cc.y) << 5) | lane;

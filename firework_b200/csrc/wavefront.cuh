@@ -130,11 +130,10 @@ FW_DEV void put_hit(const PathState& ps, uint32_t slot, float3 o, float3 d, uint
     st_stream(&ps.hq[K].o[slot], make_float4(o.x, o.y, o.z, __uint_as_float(path)));
     st_stream(&ps.hq[K].d[slot], make_float4(d.x, d.y, d.z, w.t));
     st_stream(&ps.hq[K].w[slot], make_float4(__int_as_float(w.obj), __int_as_float(w.h.prim), __int_as_float(material), __int_as_float(w.rank)));
-    if (ps.hq[K].b) st_stream(&ps.hq[K].b[slot], make_float4(w.h.b0, w.h.b1, w.h.b2, 0.0f));
 }
 template <int NQ>
-FW_DEV void enqueue_hit(const PathState& ps, uint32_t* s_fill, uint32_t seg_base, int mine, float3 o, float3 d, uint32_t path,
-                        const Winner& w, int material) {
+FW_DEV uint32_t enqueue_hit(const PathState& ps, uint32_t* s_fill, uint32_t seg_base, int mine, float3 o, float3 d, uint32_t path,
+                            const Winner& w, int material) {
     uint32_t slot = seg_reserve<NQ>(s_fill, seg_base, mine);
     switch (mine) {   // one arm per queue keeps the queue index a compile-time constant
         case 0: put_hit<0>(ps, slot, o, d, path, w, material); break;
@@ -146,6 +145,7 @@ FW_DEV void enqueue_hit(const PathState& ps, uint32_t* s_fill, uint32_t seg_base
         case FW_Q_MESH: if (NQ > FW_Q_MESH) put_hit<FW_Q_MESH>(ps, slot, o, d, path, w, material); break;
         default: break;
     }
+    return slot;   // global slot index (meaningful for lanes with 0 <= mine < NQ)
 }
 // A hit record read back by the kernel that consumes queue K.
 struct HitIn {
@@ -164,11 +164,7 @@ FW_DEV HitIn get_hit(const PathState& ps, uint32_t slot) {
     h.w.found = __float_as_int(C.x) >= 0;
     h.w.t = B.w; h.w.obj = __float_as_int(C.x); h.w.rank = __float_as_int(C.w);
     h.w.h.t = B.w; h.w.h.prim = __float_as_int(C.y);
-    h.w.h.b0 = h.w.h.b1 = h.w.h.b2 = 0.0f;
-    if (ps.hq[K].b) {   // scenes with meshes: barycentrics of the winning triangle (unused for other shapes)
-        float4 D = ld_stream(&ps.hq[K].b[slot]);
-        h.w.h.b0 = D.x; h.w.h.b1 = D.y; h.w.h.b2 = D.z;
-    }
+    h.w.h.b0 = h.w.h.b1 = h.w.h.b2 = 0.0f;   // the winning triangle's barycentrics are recomputed by finalize_hit
     return h;
 }
 

@@ -12,8 +12,9 @@ namespace fw {
 #define FW_EXTEND_MIN_BLOCKS 8   // __launch_bounds__ min blocks / SM of the BVH extend kernels (register cap knob)
 #endif
 constexpr int FW_MAX_DEPTH = 10;          // render.rs:21  `depth < 10`
-constexpr int FW_NUM_QUEUES = 8;          // [0..5] material queues (MatKind), [6] next extend queue, [7] mesh queue (two-pass extend)
-constexpr int FW_Q_EXTEND = 6, FW_Q_MESH = 7;
+constexpr int FW_NUM_QUEUES = 9;          // [0..5] material queues (MatKind), [6] next extend queue, [7] mesh queue (rays that enter
+                                          // a TriangleMesh), [8] (ray, mesh) entries of the mesh walk (counter only)
+constexpr int FW_Q_EXTEND = 6, FW_Q_MESH = 7, FW_Q_ENTRY = 8;
 constexpr int FW_TILE = 128;              // paths per tile: bounce 0 deals tiles round-robin to the segments
 #ifndef FW_BLOCK_THREADS
 #define FW_BLOCK_THREADS 128
@@ -24,12 +25,11 @@ struct HitQueue {      // one shade queue: records of the paths whose ray hit a 
     float4* o;         // [nseg][seg_cap] ray origin.xyz, asfloat(path)
     float4* d;         // ray direction.xyz (never normalised: ray.rs), winning t        (miss queue: d.xyz, asfloat(path))
     float4* w;         // asfloat(object), asfloat(primitive), asfloat(material), asfloat(rank)   (rank: two-pass extend only)
-    float4* b;         // triangle barycentrics b0, b1, b2 — allocated only for scenes with TriangleMesh objects
 };
 struct PathState {
     float4* xo[2];     // ping-pong extend queues: ray origin.xyz, asfloat(path)
     float4* xd[2];     //                          ray direction.xyz
-    HitQueue hq[8];    // [0..5] per-material shade queues (MatKind; MAT_MISS uses .d only), [7] mesh queue (two-pass extend)
+    HitQueue hq[8];    // [0..5] per-material shade queues (MatKind; MAT_MISS uses .d only), [7] mesh queue
     float4* atten;     // [FW_MAX_DEPTH][cap] attenuation chain, by path (see fold_radiance)
     float4* radiance;  // [cap] finished path radiance, by path
     uint32_t* counters;                // [FW_MAX_DEPTH + 2][FW_NUM_QUEUES][nseg] fill counts

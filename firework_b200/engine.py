@@ -106,6 +106,12 @@ class NativeScene:
         N.check(N.lib().fw_scene_linear_program(self._h, N.ptr(out), n))
         return out
 
+    def walk_info(self):
+        """{usable, top_meshes, top_wide_depth, mesh_wide_depth, prim_bits, triangles} (fw_scene_walk_info)."""
+        out = np.zeros(6, np.int32)
+        N.check(N.lib().fw_scene_walk_info(self._h, N.ptr(out)))
+        return dict(zip(("usable", "top_meshes", "top_wide_depth", "mesh_wide_depth", "prim_bits", "triangles"), (int(v) for v in out)))
+
     def material_texture(self, material):
         return N.lib().fw_material_texture(self._h, material)
 

@@ -96,6 +96,10 @@ int fw_scene_bvh_nodes(const fw_scene* scene, float* out_nodes, int capacity_nod
  * encoding in firework_b200/csrc/fw_types.h LinItem).  Copies up to `capacity_words` words (4 floats each) and
  * returns the program's length in words. */
 int fw_scene_linear_program(const fw_scene* scene, float* out_words, int capacity_words);
+/* Facts that decide whether the mesh-walk kernels serve the scene (firework_b200/csrc/walk.cuh): out = {usable, top-level
+ * TriangleMesh objects, depth of the 4-wide top-level tree, depth of the deepest 4-wide mesh tree, primitive bits of the
+ * 64-bit hit key, triangle slots}. */
+int fw_scene_walk_info(const fw_scene* scene, int out[6]);
 
 /* ---- the hot path -------------------------------------------------------------------------------------
  * replaces: the per-pixel loop of Renderer::render (src/render.rs:123-196).

@@ -4,8 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from firework_b200.engine import NativeScene
 from firework_b200.scenes import CONFIGS, SCENE_DIR
 ASSETS = os.path.join(SCENE_DIR, "assets")
-DEFAULT = {"random_spheres": (960, 540, 32), "cornell_box": (300, 300, 256), "suzanne": (1920, 1080, 8), "teapot": (1920, 1080, 8),
-           "part2_all": (1920, 1080, 8), "earth": (800, 800, 32), "hdri_test": (500, 250, 128), "conics_cli": (960, 540, 32), "volume": (960, 540, 32)}
+DEFAULT = {"random_spheres": (960, 540, 32), "cornell_box": (300, 300, 256), "suzanne": (1920, 1080, 16), "teapot": (1920, 1080, 16),
+           "part2_all": (3840, 2160, 8), "earth": (800, 800, 32), "hdri_test": (500, 250, 128), "conics_cli": (960, 540, 32), "volume": (960, 540, 32)}
 def run(name):
     cfg = CONFIGS[name]; p = cfg.path()
     w, h, spp = DEFAULT[name]
