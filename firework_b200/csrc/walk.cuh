@@ -33,14 +33,18 @@ namespace fw {
 #define FW_WALK_MIN_BLOCKS 6      // __launch_bounds__ min blocks / SM of the walk kernels (register cap knob)
 #endif
 #ifndef FW_WALK_REFILL_IDLE
-#define FW_WALK_REFILL_IDLE 12    // refill a warp when at least this many of its lanes have no node left to visit
+#define FW_WALK_REFILL_IDLE 8     // refill a warp when at least this many of its lanes can take a new entry
 #endif
 #ifndef FW_WALK_CHECKS
 #define FW_WALK_CHECKS 0          // 1 = bounds checks with printf + trap in the walk kernels (debug builds)
 #endif
 #define FW_WALK_CHECK(cond, ...) do { if (FW_WALK_CHECKS && !(cond)) { printf(__VA_ARGS__); __trap(); } } while (0)
 constexpr int FW_WALK_STACK = 64;      // deferred interior children per lane (3 per wide level; checked at flatten)
-constexpr int FW_WALK_PAIRS = 160;     // < 32 left over + at most 4 new per lane
+constexpr int FW_WALK_RING = 256;      // pair ring (power of two): < 32 left over + at most 4 new per lane = 159 in flight
+#ifndef FW_WALK_FLUSH_BLOCKED
+#define FW_WALK_FLUSH_BLOCKED 20  // test a partial batch when this many lanes can neither walk nor fetch
+#endif
+constexpr int FW_WALK_SLOTS = 64;      // entry slots per warp: two per lane
 constexpr int FW_WALK_WARPS = FW_BLOCK / 32;
 constexpr unsigned long long FW_KEY_NONE = ~0ull;
 
@@ -55,15 +59,15 @@ FW_DEV int key_rank(unsigned long long k, int prim_bits) { return (int)((~(uint3
 FW_DEV int key_prim(unsigned long long k, int prim_bits) { return (int)((~(uint32_t)k) & ((1u << prim_bits) - 1u)); }
 FW_DEV float key_bound(unsigned long long k) { return k == FW_KEY_NONE ? FW_FLT_MAX : cull_bound(key_t(k)); }
 
-// Per-warp scratch in shared memory: the rays the warp currently owns (read by whichever lane tests one of their
-// pairs), their keys, and the pair buffer.
+// Per-warp scratch in shared memory: the entries the warp currently owns (read by whichever lane tests one of their
+// pairs), their keys, and the pair ring.
 struct WalkWarp {
-    unsigned long long key[32];
-    float ox[32], oy[32], oz[32], dx[32], dy[32], dz[32];
-    uint32_t a0[32], a1[32];        // top level: path, -      mesh level: first triangle slot of the mesh, rank
-    float su_x[32], su_y[32], su_z[32];
-    int su_k[32];                   // mesh level: TriSetup of the ray in the mesh's space (mesh.rs:146-163)
-    uint32_t pairs[FW_WALK_PAIRS];  // (~leaf code) << 5 | owning lane
+    unsigned long long key[FW_WALK_SLOTS];
+    float ox[FW_WALK_SLOTS], oy[FW_WALK_SLOTS], oz[FW_WALK_SLOTS];   // ray origin in mesh space, permuted to (kx, ky, kz)
+    uint32_t a0[FW_WALK_SLOTS], a1[FW_WALK_SLOTS];                    // first triangle slot of the mesh, top-level rank
+    float su_x[FW_WALK_SLOTS], su_y[FW_WALK_SLOTS], su_z[FW_WALK_SLOTS];
+    int su_k[FW_WALK_SLOTS];                                          // TriSetup of the ray in the mesh's space (mesh.rs:146-163)
+    uint32_t pairs[FW_WALK_RING];                                     // (~leaf code) << 6 | owning slot
 };
 
 struct WalkAux {
@@ -150,20 +154,20 @@ FW_DEV void walk_visit(const float4* __restrict__ nodes, int& node, float3 o, fl
     node = (t0 < miss) ? c0 : -1;
 }
 
-// Appends the leaf children a lane found (l0..l3 of cc) to the warp's pair buffer; returns the new pair count.
-// All 32 lanes must call (lanes without work pass false flags).
-FW_DEV int walk_emit(WalkWarp& W, int npairs, bool l0, bool l1, bool l2, bool l3, int4 cc) {
+// Appends the leaf children a lane found (l0..l3 of cc) for its entry slot `slot` to the warp's pair ring; returns the new
+// tail.  All 32 lanes must call (lanes without work pass false flags).
+FW_DEV uint32_t walk_emit(WalkWarp& W, uint32_t tail, uint32_t slot, bool l0, bool l1, bool l2, bool l3, int4 cc) {
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const int c = (int)l0 + (int)l1 + (int)l2 + (int)l3;
     const unsigned b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2), b2 = __ballot_sync(0xffffffffu, c & 4);
-    if ((b0 | b1 | b2) == 0u) return npairs;
-    FW_WALK_CHECK(npairs + __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) <= FW_WALK_PAIRS, "pair buffer overflow %d\n", npairs);
-    int off = npairs + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-    if (l0) W.pairs[off++] = ((uint32_t)(~cc.x) << 5) | lane;
-    if (l1) W.pairs[off++] = ((uint32_t)(~cc.y) << 5) | lane;
-    if (l2) W.pairs[off++] = ((uint32_t)(~cc.z) << 5) | lane;
-    if (l3) W.pairs[off++] = ((uint32_t)(~cc.w) << 5) | lane;
-    return npairs + __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    if ((b0 | b1 | b2) == 0u) return tail;
+    uint32_t off = tail + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+    const uint32_t m = FW_WALK_RING - 1;
+    if (l0) W.pairs[off++ & m] = ((uint32_t)(~cc.x) << 6) | slot;
+    if (l1) W.pairs[off++ & m] = ((uint32_t)(~cc.y) << 6) | slot;
+    if (l2) W.pairs[off++ & m] = ((uint32_t)(~cc.z) << 6) | slot;
+    if (l3) W.pairs[off++ & m] = ((uint32_t)(~cc.w) << 6) | slot;
+    return tail + __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
 }
 
 }  // namespace fw
