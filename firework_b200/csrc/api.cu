@@ -109,7 +109,7 @@ static void free_path_state(PathState& ps) {
     auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     for (int i = 0; i < 2; ++i) { fr(ps.xo[i]); fr(ps.xd[i]); }
     for (HitQueue& q : ps.hq) { fr(q.o); fr(q.d); fr(q.w); }
-    fr(ps.atten); fr(ps.radiance); fr(ps.counters);
+    fr(ps.atten); fr(ps.radiance); fr(ps.counters); fr(ps.poison);
 }
 static void free_walk(RenderCtx* c) {
     if (c->walk.tkey) cudaFree(c->walk.tkey);
@@ -406,7 +406,7 @@ static int commit_uploads(fw_scene* sc) {
     const HostFlat& F = sc->flat;
     int rc;
 #define UP(field) if ((rc = upload(sc, F.field, &D.field)) != FW_OK) return rc
-    UP(nodes); UP(top_items); UP(leaf_posr); UP(leaf_meta); UP(obj_posr); UP(obj_meta); UP(obj_rot); UP(obj_irot); UP(shapes); UP(meshes);
+    UP(nodes); UP(top_leaves); UP(top_items); UP(leaf_posr); UP(leaf_meta); UP(obj_posr); UP(obj_meta); UP(obj_rot); UP(obj_irot); UP(shapes); UP(meshes);
     UP(tri_verts); UP(tri_perm); UP(tri_normals); UP(tri_uvs); UP(mats); UP(texs);
 #undef UP
     std::vector<ImageRec> images(std::max<size_t>(sc->desc.assets.size(), 1));
@@ -438,6 +438,7 @@ static int commit_uploads(fw_scene* sc) {
     D.n_objects = (int)sc->desc.objects.size();
     D.n_nodes = (int)(F.nodes.size() / 8);
     D.n_tris = (int)(F.tri_verts.size() / 3);
+    D.n_top_leaves = (int)(F.top_leaves.size() / 2);
     {
         int rc_bits = F.top_root_code;
         float rcf;
@@ -450,7 +451,15 @@ static int commit_uploads(fw_scene* sc) {
     D.has_unbounded = F.has_unbounded ? 1 : 0;
     D.nan_bvh_obj = F.nan_bvh_obj; D.nan_bvh_prim = F.nan_bvh_prim;
     D.nan_lin_obj = F.nan_lin_obj; D.nan_lin_prim = F.nan_lin_prim;
-    for (int k = 0; k < FW_MAX_WALK_MESHES; ++k) D.mesh_rank[k] = F.mesh_rank[k];
+    for (int k = 0; k < FW_MAX_WALK_MESHES; ++k) {
+        D.mesh_rank[k] = F.mesh_rank[k];
+        D.mesh_root[k] = D.mesh_tri0[k] = 0;
+        if (F.walk_ok && k < F.n_top_meshes) {
+            const ShapeRec& sh = F.shapes[F.obj_meta[F.top_items[F.mesh_rank[k]]].z];
+            D.mesh_root[k] = F.meshes[sh.i0].root_code;
+            D.mesh_tri0[k] = F.meshes[sh.i0].tri_first;
+        }
+    }
     for (const MatRec& m : F.mats) sc->mat_present[m.kind] = true;
     {
         // render.rs:31 with a black ColorEnv: an escaping path returns attenuation-chain * 0.  That is exactly 0
@@ -467,6 +476,8 @@ static int commit_uploads(fw_scene* sc) {
             if (m.kind == MAT_METAL && !(small(m.albedo[0]) && small(m.albedo[1]) && small(m.albedo[2]))) ok = false;
         if (const char* e = getenv("FW_SKIP_ZERO_MISS")) ok = ok && atoi(e) != 0;
         sc->miss_is_zero = ok;
+        sc->env_black = sc->desc.env_kind == ENV_COLOR && sc->desc.env_a[0] == 0.0f && sc->desc.env_a[1] == 0.0f && sc->desc.env_a[2] == 0.0f;
+        if (const char* e = getenv("FW_BLACK_ENV_SKIP")) sc->env_black = sc->env_black && atoi(e) != 0;
     }
     sc->lin_prog_ok = F.lin_words.size() <= (size_t)FW_LIN_MAX_WORDS;
     if (const char* e = getenv("FW_LINEAR_PROGRAM")) sc->lin_prog_ok = sc->lin_prog_ok && atoi(e) != 0;
@@ -474,6 +485,8 @@ static int commit_uploads(fw_scene* sc) {
     if (sc->lin_prog_ok) memcpy(sc->lin_prog.w, F.lin_words.data(), F.lin_words.size() * sizeof(float4));
     sc->plan.has_mesh = F.has_mesh; sc->plan.has_top_mesh = F.has_top_mesh; sc->plan.has_medium_mesh = F.has_medium_mesh;
     sc->plan.lin_prog_ok = sc->lin_prog_ok; sc->plan.lin_generic = F.lin_generic; sc->plan.lin_rect_tests = F.lin_rect_tests;
+    sc->plan.small_top = F.top_leaves.size() / 2 <= 16;   // few top-level leaves: scanned straight through (pass 1 of the mesh walk)
+    if (const char* e = getenv("FW_SMALL_TOP")) sc->plan.small_top = sc->plan.small_top && atoi(e) != 0;
     sc->plan.walk = F.walk_ok && F.has_top_mesh;   // mesh walk kernels (sphere-only trees stay on the lock-step kernel)
     if (const char* e = getenv("FW_WALK")) sc->plan.walk = sc->plan.walk && atoi(e) != 0;
     // uploads ran on the context's stream; renders may be issued on another one (fw_render_accumulate_device)
@@ -636,11 +649,12 @@ static int ensure_path_state(fw_scene* sc, size_t cap) {
         if (ctx->walk_ent_total < ent_total) {
             if (ctx->walk.entries) cudaFree(ctx->walk.entries);
             ctx->walk.entries = nullptr; ctx->walk_ent_total = 0;
-            FW_CUDA(cudaMalloc(&ctx->walk.entries, ent_total * 8));
+            FW_CUDA(cudaMalloc(&ctx->walk.entries, ent_total * sizeof(uint4)));
             ctx->walk_ent_total = ent_total;
         }
     }
     ctx->walk.prim_bits = sc->flat.walk_prim_bits;
+    if (!ps.poison) FW_CUDA(cudaMalloc(&ps.poison, 256));
     if (!ps.counters) FW_CUDA(cudaMalloc(&ps.counters, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * nseg_max));
     ps.cap = (uint32_t)cap;
     ctx->ps_cap = cap;
@@ -744,6 +758,7 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
     segment_geometry(sc, N, &ps.nseg, &ps.seg_cap);
     const size_t counter_bytes = sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * (size_t)ps.nseg;
     FW_CUDA(cudaMemsetAsync(ps.counters, 0, counter_bytes, st));
+    FW_CUDA(cudaMemsetAsync(ps.poison, 0, sizeof(uint32_t), st));
     unsigned sm = (unsigned)sc->sm_count;
     // FW_DEBUG_SYNC=1: synchronise after every stage and name the one that faulted (debugging aid; slow)
     static const bool debug_sync = getenv("FW_DEBUG_SYNC") != nullptr;
@@ -794,7 +809,7 @@ static int run_batch(fw_scene* sc, const CameraRec& cam, const Batch& b, uint2 s
         tot.extend_launches++;
         FW_STAGE("extend", bounce);
         if (!sc->miss_is_zero) {
-            launch_miss(S, ps, bounce, st);
+            launch_miss(S, ps, bounce, sc->env_black, st);
             tot.launches++;
             FW_STAGE("miss", bounce);
         }

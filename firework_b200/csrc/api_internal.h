@@ -79,6 +79,7 @@ struct fw_scene {
     bool mat_present[MAT_NUM_QUEUES] = {false, false, false, false, false, false};
     std::vector<HdrStaging*> hdr_staging;   // per asset: pinned RGBA copy of an HDR map (set_hdr .. commit)
     bool miss_is_zero = false;  // every escaping path contributes exactly 0: the miss kernel is not launched
+    bool env_black = false;     // black ColorEnv: the miss kernel only has work in a batch some attenuation poisoned
     RenderCtx* ctx = nullptr;  // render-time state, borrowed from the per-device cache at commit
     size_t batch_paths = 0;    // 0 = default
     bool profiling = false;

@@ -106,6 +106,8 @@ struct EnvRec {
 struct DeviceScene {
     const float4* nodes;       // wide nodes of all trees (top-level tree first)
     float4 top_lo, top_hi;     // the top-level root's box; top_lo.w = asfloat(root code)
+    const float4* top_leaves;  // 2 per top-level leaf, DFS order: (box min, asfloat(first rank)), (box max, asfloat(item count))
+    int n_top_leaves;
     const int* top_items;      // object ids in top-level DFS leaf order (rank = tie-break key, bvh.rs:128,141)
     const float4* leaf_posr;   // obj_posr reordered by top-level DFS leaf rank (no indirection in the leaf loop)
     const int4* leaf_meta;     // obj_meta reordered by rank; .w = object id
@@ -134,6 +136,8 @@ struct DeviceScene {
     // object id (-1 = miss) and primitive (mesh: last triangle slot, Rect3d: last face), for BVH and linear roots.
     int nan_bvh_obj, nan_bvh_prim, nan_lin_obj, nan_lin_prim;
     int mesh_rank[FW_MAX_WALK_MESHES];   // top-level DFS rank of the mesh object with ordinal k (scenes with <= 8 top-level meshes)
+    int mesh_root[FW_MAX_WALK_MESHES];   // ... the root (wide node) of its triangle tree
+    int mesh_tri0[FW_MAX_WALK_MESHES];   // ... its first triangle slot
 };
 
 struct CameraRec {  // camera.rs:7-16

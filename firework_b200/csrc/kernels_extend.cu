@@ -68,12 +68,87 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass1_k
                 m &= m - 1u;
                 const uint32_t e = atomicAdd(&s_fill[FW_Q_ENTRY], 1u);
                 FW_WALK_CHECK(e < aux.ent_cap && ord < FW_MAX_WALK_MESHES, "entry overflow e=%u cap=%u ord=%d\n", e, aux.ent_cap, ord);
-                aux.entries[(size_t)seg * aux.ent_cap + e] = make_uint2(slot - seg_base, (uint32_t)S.mesh_rank[ord]);
+                aux.entries[(size_t)seg * aux.ent_cap + e] = make_uint4(slot - seg_base, (uint32_t)S.mesh_rank[ord], (uint32_t)S.mesh_root[ord], (uint32_t)S.mesh_tri0[ord]);
             }
         }
     }
     seg_close<FW_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), seg);
 }
+// The same pass for scenes whose top-level tree has only a handful of leaves (a floor, a light, a few meshes): no walk at
+// all.  A leaf of the reference's tree is reached iff its own box test passes (every ancestor's box contains it and the
+// slab arithmetic is monotonic in the box planes), so the leaves are scanned in DFS order — every lane of the warp at the
+// same leaf — and hits are merged by the (t, rank) rule of bvh.rs:120-146, which in rank order is "later wins unless
+// strictly farther".  No stack, no traversal divergence; always with ENTRIES (it only serves the mesh walk).
+template <bool NESTED>
+__global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass1_small_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
+                                                                                      uint32_t bounce, WalkAux aux) {
+    __shared__ uint32_t s_fill[FW_NUM_QUEUES];
+    const uint32_t seg = blockIdx.x;
+    const uint32_t in_count = counter_row(ps, bounce, FW_Q_EXTEND)[seg];
+    seg_open<FW_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), seg);
+    const uint32_t seg_base = seg * ps.seg_cap;
+    const float tmin = 0.001f, tmax = 2e9f;   // render.rs:19
+    for (uint32_t e0 = 0; e0 < in_count; e0 += FW_BLOCK) {
+        const bool valid = e0 + threadIdx.x < in_count;
+        uint32_t path = 0, pending = 0u;
+        float3 o = f3(1e30f, 1e30f, 1e30f), d = f3(1.0f, 1.0f, 1.0f);
+        Winner w;
+        w.found = false; w.t = 0.0f; w.obj = -1; w.rank = -1; w.h.t = 0.0f; w.h.prim = 0;
+        w.h.b0 = w.h.b1 = w.h.b2 = 0.0f;
+        int mine = -1, material = -1;
+        if (valid) {
+            const size_t slot_in = (size_t)seg_base + e0 + threadIdx.x;
+            float4 ro = ld_stream(&ps.xo[bounce & 1][slot_in]), rd = ld_stream(&ps.xd[bounce & 1][slot_in]);
+            o = f3(ro); d = f3(rd); path = __float_as_uint(ro.w);
+            if (nan_direction(d)) {
+                nan_direction_winner(S.nan_bvh_obj, S.nan_bvh_prim, w);
+            } else {
+                RngKey key{seed, 0u, 0u, bounce};
+                if (S.has_medium) batch_path(b, path, key.pixel, key.sample);
+                const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                float bnd = FW_FLT_MAX;
+                for (int l = 0; l < S.n_top_leaves; ++l) {
+                    const float4 lo = __ldg(&S.top_leaves[2 * l]), hi = __ldg(&S.top_leaves[2 * l + 1]);
+                    float te;
+                    if (!slab_test(lo, hi, o, inv, tmin, tmax, te)) continue;
+                    const int first = as_int(lo.w), count = as_int(hi.w);
+                    for (int k = 0; k < count; ++k) {
+                        const int rank = first + k;
+                        const float4 posr = __ldg(&S.leaf_posr[rank]);
+                        const int4 meta = __ldg(&S.leaf_meta[rank]);
+                        if ((meta.x & OBJ_KIND_MASK) == SH_MESH) {
+                            if (mesh_root_box_hit(S, posr, meta, o, d, bnd)) pending |= 1u << ((meta.x >> OBJ_MESH_ORD_SHIFT) & (FW_MAX_WALK_MESHES - 1));
+                            continue;
+                        }
+                        ObjHit h;
+                        if (object_test_loaded<false, NESTED>(S, meta.w, posr, meta, o, d, tmin, tmax, bnd, key, h, nullptr)) {
+                            if (!w.found || !(w.t < h.t)) {   // ranks ascend: the later item wins unless it is strictly farther
+                                w.found = true; w.t = h.t; w.obj = meta.w; w.rank = rank; w.h = h;
+                                bnd = top_bound(S, h.t);
+                            }
+                        }
+                    }
+                }
+            }
+            if (pending) mine = FW_Q_MESH;
+            else mine = classify_winner(S, w, material);
+        }
+        const uint32_t slot = enqueue_hit<FW_Q_MESH + 1>(ps, s_fill, seg_base, mine, o, d, path, w, material);
+        if (pending) {
+            aux.tkey[slot] = w.found ? pack_key(w.t, w.rank, w.h.prim, aux.prim_bits) : FW_KEY_NONE;
+            uint32_t m = pending;
+            while (m) {
+                const int ord = __ffs(m) - 1;
+                m &= m - 1u;
+                const uint32_t e = atomicAdd(&s_fill[FW_Q_ENTRY], 1u);
+                FW_WALK_CHECK(e < aux.ent_cap && ord < FW_MAX_WALK_MESHES, "entry overflow e=%u cap=%u ord=%d\n", e, aux.ent_cap, ord);
+                aux.entries[(size_t)seg * aux.ent_cap + e] = make_uint4(slot - seg_base, (uint32_t)S.mesh_rank[ord], (uint32_t)S.mesh_root[ord], (uint32_t)S.mesh_tri0[ord]);
+            }
+        }
+    }
+    seg_close<FW_NUM_QUEUES>(s_fill, ps, counter_row(ps, bounce, 0), seg);
+}
+
 template <bool NESTED>
 __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass2_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
                                                                                 uint32_t bounce) {
@@ -191,10 +266,15 @@ int launch_extend(const ExtendPlan& plan, bool use_bvh, const LinProgram& P, con
     }
     return 1;
 }
-void launch_extend_pass1_entries(bool nested, const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce,
+void launch_extend_pass1_entries(bool small_top, bool nested, const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce,
                                  const WalkAuxHost& ax, cudaStream_t st) {
     WalkAux aux;
-    aux.tkey = ax.tkey; aux.entries = reinterpret_cast<uint2*>(ax.entries); aux.ent_cap = ax.ent_cap; aux.prim_bits = ax.prim_bits;
+    aux.tkey = ax.tkey; aux.entries = reinterpret_cast<uint4*>(ax.entries); aux.ent_cap = ax.ent_cap; aux.prim_bits = ax.prim_bits;
+    if (small_top) {
+        if (nested) extend_pass1_small_kernel<true><<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, aux);
+        else extend_pass1_small_kernel<false><<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, aux);
+        return;
+    }
     if (nested) extend_pass1_kernel<true, true><<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, aux);
     else extend_pass1_kernel<false, true><<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, b, seed, bounce, aux);
 }

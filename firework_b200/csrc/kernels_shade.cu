@@ -50,7 +50,13 @@ FW_DEV float3 fold_radiance(const PathState& ps, uint32_t path, uint32_t bounce,
 }
 
 // render.rs:31 — environment lookup for rays that left the scene
+// BLACK_ENV: the environment is a black ColorEnv, so an escaping path returns chain * 0 = exactly 0 — which the radiance
+// buffer already holds — unless some attenuation of the batch was NaN / inf / huge (NaN * 0 = NaN must survive, e.g. noise
+// textures evaluated at a non-finite hit point).  The shade kernels raise ps.poison for such a value; without it the
+// whole kernel is a no-op and returns at once (no attenuation chain is read at all).
+template <bool BLACK_ENV>
 __global__ void __launch_bounds__(FW_BLOCK) miss_kernel(DeviceScene S, PathState ps, uint32_t bounce) {
+    if (BLACK_ENV && *reinterpret_cast<volatile uint32_t*>(ps.poison) == 0u) return;
     const uint32_t total = counter_row(ps, bounce, MAT_MISS)[blockIdx.x];
     const float4* qd = ps.hq[MAT_MISS].d + (size_t)blockIdx.x * ps.seg_cap;
     for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
@@ -127,6 +133,8 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_SHADE_MIN_BLOCKS) shade_scatter_k
                 st_stream(&ps.atten[(size_t)bounce * ps.cap + path],
                           make_float4(out.attenuation.x, out.attenuation.y, out.attenuation.z, 0.0f));
                 mine = 0;
+                // ten factors of magnitude <= 1e3 can not overflow; anything else (NaN included) poisons the batch
+                if (!(fabsf(out.attenuation.x) <= 1e3f && fabsf(out.attenuation.y) <= 1e3f && fabsf(out.attenuation.z) <= 1e3f)) *ps.poison = 1u;
             }
             // absorbed (metal below the surface): radiance stays 0 (render.rs:25)
         }
@@ -193,8 +201,9 @@ __global__ void __launch_bounds__(256) resolve_kernel(const float* __restrict__ 
 void launch_raygen(const CameraRec& cam, const Batch& b, uint2 seed, const PathState& ps, cudaStream_t st) {
     raygen_kernel<<<ps.nseg, FW_BLOCK, 0, st>>>(cam, b, seed, ps);
 }
-void launch_miss(const DeviceScene& S, const PathState& ps, uint32_t bounce, cudaStream_t st) {
-    miss_kernel<<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, bounce);
+void launch_miss(const DeviceScene& S, const PathState& ps, uint32_t bounce, bool black_env, cudaStream_t st) {
+    if (black_env) miss_kernel<true><<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, bounce);
+    else miss_kernel<false><<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, bounce);
 }
 void launch_shade_emissive(const DeviceScene& S, const PathState& ps, uint32_t bounce, cudaStream_t st) {
     shade_emissive_kernel<<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, bounce);

@@ -22,11 +22,6 @@ FW_DEV void winner_from_key(const DeviceScene& S, unsigned long long k, int prim
 // One work item = one (ray, mesh) entry: the mesh's tree is walked in the mesh's object space (scene.rs:242-253),
 // triangles are tested in the test phase (mesh.rs:140-219), and the entry's best (t, rank, slot) is merged into the
 // ray's key in global memory.
-//
-// Every lane owns TWO entry slots of its warp's shared scratch (lane, lane + 32) and alternates between them: while the
-// pairs of the entry it has just finished walking are still waiting in the (FIFO) pair ring, it already walks the next
-// entry in its other slot.  A slot is recycled once the ring's head has passed the lane's last emission for it, so a
-// refill never has to flush the ring, and the test phase runs on full batches of 32 pairs except at the very end.
 __global__ void __launch_bounds__(FW_BLOCK, FW_WALK_MIN_BLOCKS) walk_mesh_kernel(DeviceScene S, PathState ps, uint32_t bounce,
                                                                                  WalkAux aux) {
     __shared__ uint32_t s_cursor;
@@ -41,49 +36,31 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_WALK_MIN_BLOCKS) walk_mesh_kernel
     const size_t seg_base = (size_t)seg * ps.seg_cap;
     const float4* __restrict__ qo = ps.hq[FW_Q_MESH].o + seg_base;   // the rays that enter a mesh (pass 1)
     const float4* __restrict__ qd = ps.hq[FW_Q_MESH].d + seg_base;
-    const uint2* __restrict__ ents = aux.entries + (size_t)seg * aux.ent_cap;
+    const uint4* __restrict__ ents = aux.entries + (size_t)seg * aux.ent_cap;
     unsigned long long* __restrict__ tkey = aux.tkey + seg_base;
     const float tmin = 0.001f, tmax = 2e9f;
     const int pb = aux.prim_bits;
 
-    // walker state of the entry in the current slot
-    bool active = false;
+    bool has_ray = false, active = false;
     float3 o = f3(0.0f, 0.0f, 0.0f), inv = f3(1.0f, 1.0f, 1.0f);   // the entry's ray in mesh space, permuted to (kx, ky, kz)
     uint32_t near_pack = 0, far_pack = 0;                           // node row offsets for that permutation (walk_rows)
     float bound0 = FW_FLT_MAX;                                      // FW_WALK_CULL == 0: the bound pass 1 left
     int node = -1, sp = 0;
-    int stk_code[FW_WALK_STACK];
-    float stk_te[FW_WALK_STACK];
-    // the lane's two slots: cur = lane + 32 * par is being walked (or was walked last), the other one drains
-    uint32_t par = 0;
-    bool occ_a = false, occ_b = false;          // slot lane / lane + 32 holds an entry that has not been retired
-    uint32_t lp_a = 0, lp_b = 0;                // ring position after the lane's last emission for that slot
-    uint32_t si_a = 0, si_b = 0;                // the entry's ray (slot in the segment's mesh queue)
-    uint32_t head = 0, tail = 0;                // pair ring (uniform across the warp); pairs live at index & (FW_WALK_RING - 1)
+    uint32_t slot_in = 0;
+    unsigned long long stk[FW_WALK_STACK];   // deferred interior children: (cull distance, node)
+    int npairs = 0;
     bool input_left = true;
 
-    auto retire = [&](uint32_t slot, uint32_t ray) {   // merge the slot's best into the ray's key
-        const unsigned long long k = W.key[slot];
-        if (k != FW_KEY_NONE) atomicMin(&tkey[ray], k);
-    };
-
     for (;;) {
-        const unsigned act = __ballot_sync(0xffffffffu, active);
-        const int npairs = (int)(tail - head);
-        // a lane without a node can take a new entry once its OTHER slot is free or fully drained
-        const bool other_occ = par ? occ_a : occ_b;
-        const bool other_ok = !other_occ || (int)(head - (par ? lp_a : lp_b)) >= 0;
-        const unsigned can = __ballot_sync(0xffffffffu, !active && input_left && other_ok);
-        const bool refill = can != 0u && (__popc(can) >= FW_WALK_REFILL_IDLE || act == 0u);
-        // flush a partial batch only when most of the warp is blocked behind it (or nothing else is left to do)
-        const bool flush = npairs > 0 && !refill && (act == 0u || (input_left && 32 - __popc(act) - __popc(can) >= FW_WALK_FLUSH_BLOCKED));
-        if (npairs >= 32 || flush) {
+        unsigned act = __ballot_sync(0xffffffffu, active);
+        const bool want_refill = (input_left && 32 - __popc(act) >= FW_WALK_REFILL_IDLE) || act == 0u;
+        if (npairs >= 32 || (want_refill && npairs > 0)) {
             // ---- TEST: one pair per lane, the leaf's 1-2 triangles against the owning entry's ray (bvh.rs:119-133 over
             // Triangle items, mesh.rs:140-219)
             const int n = npairs < 32 ? npairs : 32;
             __syncwarp();
             if ((int)lane < n) {
-                const uint32_t pr = W.pairs[(head + lane) & (FW_WALK_RING - 1)];
+                const uint32_t pr = W.pairs[npairs - n + lane];
                 const unsigned src = pr & 63u;
                 const int packed = (int)(pr >> 6);
                 const int first = packed >> 1, count = (packed & 1) + 1;
@@ -91,9 +68,9 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_WALK_MIN_BLOCKS) walk_mesh_kernel
                 TriSetup su;
                 su.kz = W.su_k[src]; su.sx = W.su_x[src]; su.sy = W.su_y[src]; su.sz = W.su_z[src];
                 const int tri_first = (int)W.a0[src], rank = (int)W.a1[src];
+                // vertices from the copy permuted for this ray's dominant axis; the origin was stored permuted at fetch
                 FW_WALK_CHECK(su.kz >= 0 && su.kz < 3 && tri_first >= 0 && first >= 0 && tri_first + first + count <= S.n_tris,
                               "bad pair kz=%d tri_first=%d first=%d count=%d n_tris=%d pr=%08x\n", su.kz, tri_first, first, count, S.n_tris, pr);
-                // vertices from the copy permuted for this ray's dominant axis; the origin was stored permuted at fetch
                 const float4* tv = S.tri_perm + ((size_t)su.kz * S.n_tris + tri_first) * 3;
                 for (int k = 0; k < count; ++k) {
                     const int slot = first + k;
@@ -104,89 +81,84 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_WALK_MIN_BLOCKS) walk_mesh_kernel
                         atomicMin(&W.key[src], pack_key(t, rank, slot, pb));
                 }
             }
-            head += (uint32_t)n;
+            npairs -= n;
             __syncwarp();
             continue;
         }
-        if (refill) {
-            const unsigned want = can;   // uniform: the lanes that fetch now
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&s_cursor, (uint32_t)__popc(want));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if ((want >> lane) & 1u) {
-                // recycle the other slot (its pairs have all been tested), then make it the current one
-                if (other_occ) retire(lane + (par ? 0u : 32u), par ? si_a : si_b);
-                par ^= 1u;
-                if (par) occ_b = false; else occ_a = false;
-                const uint32_t e = base + __popc(want & lt);
-                if (e < in_count) {
-                    const uint32_t cur = lane + 32u * par;
-                    const uint2 en = ents[e];
-                    const uint32_t ray = en.x;
-                    const int rank = (int)en.y;
-                    FW_WALK_CHECK(ray < ps.seg_cap && rank >= 0 && rank < S.n_objects, "bad entry %u rank %d (e=%u of %u)\n", ray, rank, e, in_count);
-                    const float4 ro = __ldg(&qo[ray]), rd = __ldg(&qd[ray]);
-                    const float4 posr = __ldg(&S.leaf_posr[rank]);
-                    const int4 meta = __ldg(&S.leaf_meta[rank]);
-                    float3 oo = f3(ro) - f3(posr), od = f3(rd);
-                    if (meta.x & OBJ_ROTATED) {   // scene.rs:242-249
-                        const float4* m = &S.obj_irot[3 * meta.w];
-                        float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
-                        od = mat_mul(r0, r1, r2, f3(rd));
-                        oo = mat_mul(r0, r1, r2, oo);
-                    }
-                    const float4* q = reinterpret_cast<const float4*>(&S.shapes[meta.z]);
-                    const float4* mr = reinterpret_cast<const float4*>(&S.meshes[as_int(__ldg(q).z)]);
-                    const int4 m0 = __ldg(reinterpret_cast<const int4*>(mr));
-                    const TriSetup su = tri_setup(od);
-                    {   // walker and test phase both use the ray permuted to (kx, ky, kz) order (mesh.rs:146-153)
-                        const int kx = su.kz == 2 ? 0 : su.kz + 1, ky = kx == 2 ? 0 : kx + 1;
-                        o = f3(comp3(oo, kx), comp3(oo, ky), comp3(oo, su.kz));
-                        const float3 dp = f3(comp3(od, kx), comp3(od, ky), comp3(od, su.kz));
-                        inv = f3(1.0f / dp.x, 1.0f / dp.y, 1.0f / dp.z);
-                        walk_rows(su.kz, inv, near_pack, far_pack);
-                        W.ox[cur] = o.x; W.oy[cur] = o.y; W.oz[cur] = o.z;
-                    }
-                    bound0 = rd.w > 0.0f ? cull_bound(rd.w) : FW_FLT_MAX;   // the pass-1 winner's t travels in d.w (0: none)
-                    W.su_k[cur] = su.kz; W.su_x[cur] = su.sx; W.su_y[cur] = su.sy; W.su_z[cur] = su.sz;
-                    W.a0[cur] = (uint32_t)m0.y;   // first triangle slot
-                    W.a1[cur] = (uint32_t)rank;
-                    // the ray's best so far (top-level winner, or an earlier entry's triangle): only a culling bound here
-                    W.key[cur] = *reinterpret_cast<volatile unsigned long long*>(&tkey[ray]);
-                    if (par) { occ_b = true; si_b = ray; lp_b = head; } else { occ_a = true; si_a = ray; lp_a = head; }
-                    active = true;
-                    sp = 0;
-                    FW_WALK_CHECK(m0.x >= 0 && m0.x < S.n_nodes && (meta.x & OBJ_KIND_MASK) == SH_MESH, "bad mesh root %d kind %d rank %d\n", m0.x, meta.x & OBJ_KIND_MASK, rank);
-                    node = m0.x;   // the mesh's root (a wide node: checked at flatten); its box was tested at top level
-                }
+        if (want_refill) {
+            if (has_ray && !active) {   // retire: merge this entry's best into the ray's key
+                const unsigned long long k = W.key[lane];
+                if (k != FW_KEY_NONE) atomicMin(&tkey[slot_in], k);
+                has_ray = false;
             }
-            if (base + (uint32_t)__popc(want) >= in_count) input_left = false;
-            continue;
+            if (input_left) {
+                const unsigned want = __ballot_sync(0xffffffffu, !has_ray);
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_cursor, (uint32_t)__popc(want));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (!has_ray) {
+                    const uint32_t e = base + __popc(want & lt);
+                    if (e < in_count) {
+                        const uint4 en = __ldg(&ents[e]);
+                        slot_in = en.x;
+                        const int rank = (int)en.y;
+                        const float4 ro = __ldg(&qo[slot_in]), rd = __ldg(&qd[slot_in]);
+                        const float4 posr = __ldg(&S.leaf_posr[rank]);
+                        const int4 meta = __ldg(&S.leaf_meta[rank]);
+                        float3 oo = f3(ro) - f3(posr), od = f3(rd);
+                        if (meta.x & OBJ_ROTATED) {   // scene.rs:242-249
+                            const float4* m = &S.obj_irot[3 * meta.w];
+                            float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+                            od = mat_mul(r0, r1, r2, f3(rd));
+                            oo = mat_mul(r0, r1, r2, oo);
+                        }
+                        const int2 m0 = make_int2((int)en.z, (int)en.w);   // the mesh's root node, its first triangle slot
+                        const TriSetup su = tri_setup(od);
+                        {   // walker and test phase both use the ray permuted to (kx, ky, kz) order (mesh.rs:146-153)
+                            const int kx = su.kz == 2 ? 0 : su.kz + 1, ky = kx == 2 ? 0 : kx + 1;
+                            o = f3(comp3(oo, kx), comp3(oo, ky), comp3(oo, su.kz));
+                            const float3 dp = f3(comp3(od, kx), comp3(od, ky), comp3(od, su.kz));
+                            inv = f3(1.0f / dp.x, 1.0f / dp.y, 1.0f / dp.z);
+                            walk_rows(su.kz, inv, near_pack, far_pack);
+                            W.ox[lane] = o.x; W.oy[lane] = o.y; W.oz[lane] = o.z;
+                        }
+                        bound0 = rd.w > 0.0f ? cull_bound(rd.w) : FW_FLT_MAX;   // the pass-1 winner's t travels in d.w (0: none)
+                        W.su_k[lane] = su.kz; W.su_x[lane] = su.sx; W.su_y[lane] = su.sy; W.su_z[lane] = su.sz;
+                        W.a0[lane] = (uint32_t)m0.y;   // first triangle slot
+                        W.a1[lane] = (uint32_t)rank;
+                        // the ray's best so far (top-level winner, or an earlier entry's triangle): only a culling bound here
+                        W.key[lane] = *reinterpret_cast<volatile unsigned long long*>(&tkey[slot_in]);
+                        has_ray = true;
+                        active = true;
+                        sp = 0;
+                        FW_WALK_CHECK(m0.x >= 0 && m0.x < S.n_nodes && (meta.x & OBJ_KIND_MASK) == SH_MESH, "bad mesh root %d kind %d rank %d\n", m0.x, meta.x & OBJ_KIND_MASK, rank);
+                        node = m0.x;   // the mesh's root (a wide node: checked at flatten); its box was tested at top level
+                    }
+                }
+                if (base + (uint32_t)__popc(want) >= in_count) input_left = false;
+            }
+            act = __ballot_sync(0xffffffffu, active);
+            if (act == 0u) {
+                if (!input_left && __ballot_sync(0xffffffffu, has_ray) == 0u) break;
+                continue;
+            }
         }
-        if (act == 0u) break;   // no node, no pair, no entry left to fetch (npairs == 0 here: it would have been flushed)
-        // ---- WALK: one wide-node visit per lane that has a node
         bool l0 = false, l1 = false, l2 = false, l3 = false;
         int4 cc = make_int4(0, 0, 0, 0);
-        const uint32_t cur = lane + 32u * par;
         if (active) {
-            const float bnd = FW_WALK_CULL == 0 ? bound0 : key_bound(W.key[cur]);
+            const float bnd = FW_WALK_CULL == 0 ? bound0 : key_bound(W.key[lane]);
             if (node < 0) {
                 for (;;) {
                     if (sp == 0) { active = false; break; }
-                    --sp;
-                    if (!(stk_te[sp] > bnd)) { node = stk_code[sp]; break; }
+                    const unsigned long long e = stk[--sp];
+                    if (!(__uint_as_float((uint32_t)(e >> 32)) > bnd)) { node = (int)(uint32_t)e; break; }
                 }
             }
             FW_WALK_CHECK(!active || (node >= 0 && node < S.n_nodes), "bad node %d sp %d\n", node, sp);
-            if (active) walk_visit(S.nodes, node, o, inv, near_pack, far_pack, bnd, stk_code, stk_te, sp, l0, l1, l2, l3, cc);
+            if (active) walk_visit(S.nodes, node, o, inv, near_pack, far_pack, bnd, stk, sp, l0, l1, l2, l3, cc);
         }
-        const uint32_t new_tail = walk_emit(W, tail, cur, l0, l1, l2, l3, cc);
-        if (l0 | l1 | l2 | l3) { if (par) lp_b = new_tail; else lp_a = new_tail; }
-        tail = new_tail;
+        npairs = (int)walk_emit(W, (uint32_t)npairs, lane, l0, l1, l2, l3, cc);
     }
-    // ---- the end: every pair has been tested (the loop only leaves with an empty ring); retire what is still held
-    if (occ_a) retire(lane, si_a);
-    if (occ_b) retire(lane + 32u, si_b);
 }
 
 // ---- classification of the rays that entered a mesh ------------------------------------------------------------------
@@ -223,9 +195,9 @@ __global__ void __launch_bounds__(FW_BLOCK) classify_mesh_kernel(DeviceScene S, 
 void launch_extend_walk_part(int part, const ExtendPlan& plan, const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed,
                              uint32_t bounce, const WalkAuxHost& ax, cudaStream_t st) {
     WalkAux aux;
-    aux.tkey = ax.tkey; aux.entries = reinterpret_cast<uint2*>(ax.entries); aux.ent_cap = ax.ent_cap; aux.prim_bits = ax.prim_bits;
+    aux.tkey = ax.tkey; aux.entries = reinterpret_cast<uint4*>(ax.entries); aux.ent_cap = ax.ent_cap; aux.prim_bits = ax.prim_bits;
     const unsigned G = ps.nseg;
-    if (part == 0) launch_extend_pass1_entries(plan.has_medium_mesh, S, ps, b, seed, bounce, ax, st);
+    if (part == 0) launch_extend_pass1_entries(plan.small_top, plan.has_medium_mesh, S, ps, b, seed, bounce, ax, st);
     else if (part == 1) walk_mesh_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, bounce, aux);
     else classify_mesh_kernel<<<G, FW_BLOCK, 0, st>>>(S, ps, bounce, aux);
 }

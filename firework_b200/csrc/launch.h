@@ -19,13 +19,14 @@ struct ExtendPlan {
     bool lin_prog_ok = false;       // the linear-scan program fits kernel-parameter space
     bool lin_generic = false;       // ... and contains LIN_GENERIC items
     int lin_rect_tests = 0;         // AARect::hit calls per ray in the program
+    bool small_top = false;         // the top-level tree has so few leaves that pass 1 scans them in order instead of walking
     bool walk = false;              // BVH scenes: collect / test walk kernels (walk.cuh) instead of the lock-step ones
 };
 
 // Device buffers of the walk kernels (allocated with the path state).
 struct WalkAuxHost {
     unsigned long long* tkey = nullptr;   // [queue capacity] per-ray keys (scenes with top-level meshes)
-    void* entries = nullptr;              // uint2 [nseg_max * ent_cap] (ray slot, mesh rank)
+    void* entries = nullptr;              // uint4 [nseg_max * ent_cap] (ray slot, mesh rank, mesh root node, first triangle slot)
     uint32_t ent_cap = 0;                 // entries per segment
     int prim_bits = 0;
 };
@@ -40,11 +41,11 @@ int launch_extend_walk(const ExtendPlan& plan, const DeviceScene& S, const PathS
 // One of its three kernels on its own (0 = pass 1 with entries, 1 = mesh walk, 2 = classification): FW_DEBUG_SYNC.
 void launch_extend_walk_part(int part, const ExtendPlan& plan, const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed,
                              uint32_t bounce, const WalkAuxHost& aux, cudaStream_t st);
-void launch_extend_pass1_entries(bool nested, const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce,
+void launch_extend_pass1_entries(bool small_top, bool nested, const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce,
                                  const WalkAuxHost& aux, cudaStream_t st);
 void launch_extend_debug(const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce, uint32_t* steps,
                          cudaStream_t st);
-void launch_miss(const DeviceScene& S, const PathState& ps, uint32_t bounce, cudaStream_t st);
+void launch_miss(const DeviceScene& S, const PathState& ps, uint32_t bounce, bool black_env, cudaStream_t st);
 void launch_shade_emissive(const DeviceScene& S, const PathState& ps, uint32_t bounce, cudaStream_t st);
 void launch_shade_scatter(int mat, const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce,
                           cudaStream_t st);

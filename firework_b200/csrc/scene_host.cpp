@@ -981,6 +981,32 @@ bool flatten_scene(const SceneDesc& desc, HostFlat& out, std::string& err) {
         return false;
     }
     out.top_items = top.items;
+    {
+        // The top-level tree's leaves with the reference's boxes for them, in DFS order: small scenes scan this list
+        // straight through instead of walking the tree (kernels_extend.cu extend_pass1_small_kernel).
+        std::vector<std::pair<int, std::pair<float4, float4>>> leaves;
+        auto add_leaf = [&](int code, const float* lo, const float* hi) {
+            const int packed = ~code, first = packed >> 1, count = (packed & 1) + 1;
+            leaves.push_back({first, {float4{lo[0], lo[1], lo[2], as_float(first)}, float4{hi[0], hi[1], hi[2], as_float(count)}}});
+        };
+        if (top.root_code < 0) {
+            const float lo[3] = {top.root_box.mn.x, top.root_box.mn.y, top.root_box.mn.z}, hi[3] = {top.root_box.mx.x, top.root_box.mx.y, top.root_box.mx.z};
+            add_leaf(top.root_code, lo, hi);
+        }
+        for (size_t n = 0; n + 7 < top.nodes.size(); n += 8) {
+            const float4* q = &top.nodes[n];
+            const float* rows[6] = {&q[0].x, &q[1].x, &q[2].x, &q[3].x, &q[4].x, &q[5].x};
+            int codes[4];
+            memcpy(codes, &q[6], 16);
+            for (int k = 0; k < 4; ++k) {
+                if (codes[k] >= 0 || codes[k] == (int)0x80000000) continue;
+                const float lo[3] = {rows[0][k], rows[1][k], rows[2][k]}, hi[3] = {rows[3][k], rows[4][k], rows[5][k]};
+                add_leaf(codes[k], lo, hi);
+            }
+        }
+        std::sort(leaves.begin(), leaves.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        for (const auto& l : leaves) { out.top_leaves.push_back(l.second.first); out.top_leaves.push_back(l.second.second); }
+    }
     for (int obj : top.items) {
         out.leaf_posr.push_back(out.obj_posr[obj]);
         int4 m = out.obj_meta[obj];

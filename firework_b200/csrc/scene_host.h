@@ -74,6 +74,7 @@ bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& er
 struct HostFlat {
     std::vector<float4> nodes;
     std::vector<int> top_items;
+    std::vector<float4> top_leaves;   // 2 per top-level leaf in DFS order: (box min, asfloat(first rank)), (box max, asfloat(items))
     std::vector<float4> lin_words;  // linear-scan program (fw_types.h LinItem), END-terminated
     bool lin_generic = false;       // the program contains LIN_GENERIC items
     int lin_rect_tests = 0;         // AARect::hit calls per ray in the program (RECT items + 6 per BOX6)

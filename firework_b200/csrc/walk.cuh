@@ -33,18 +33,15 @@ namespace fw {
 #define FW_WALK_MIN_BLOCKS 6      // __launch_bounds__ min blocks / SM of the walk kernels (register cap knob)
 #endif
 #ifndef FW_WALK_REFILL_IDLE
-#define FW_WALK_REFILL_IDLE 8     // refill a warp when at least this many of its lanes can take a new entry
+#define FW_WALK_REFILL_IDLE 12    // refill a warp when at least this many of its lanes have no node left to visit
 #endif
 #ifndef FW_WALK_CHECKS
 #define FW_WALK_CHECKS 0          // 1 = bounds checks with printf + trap in the walk kernels (debug builds)
 #endif
 #define FW_WALK_CHECK(cond, ...) do { if (FW_WALK_CHECKS && !(cond)) { printf(__VA_ARGS__); __trap(); } } while (0)
 constexpr int FW_WALK_STACK = 64;      // deferred interior children per lane (3 per wide level; checked at flatten)
-constexpr int FW_WALK_RING = 256;      // pair ring (power of two): < 32 left over + at most 4 new per lane = 159 in flight
-#ifndef FW_WALK_FLUSH_BLOCKED
-#define FW_WALK_FLUSH_BLOCKED 20  // test a partial batch when this many lanes can neither walk nor fetch
-#endif
-constexpr int FW_WALK_SLOTS = 64;      // entry slots per warp: two per lane
+constexpr int FW_WALK_RING = 256;      // pair buffer (power of two): < 32 left over + at most 4 new per lane = 159 pending
+constexpr int FW_WALK_SLOTS = 32;      // entry slots per warp: one per lane
 constexpr int FW_WALK_WARPS = FW_BLOCK / 32;
 constexpr unsigned long long FW_KEY_NONE = ~0ull;
 
@@ -72,7 +69,8 @@ struct WalkWarp {
 
 struct WalkAux {
     unsigned long long* tkey;   // [nseg][seg_cap] per-ray key of the current bounce (mesh scenes)
-    uint2* entries;             // [nseg][ent_cap] (slot in the segment's extend queue, top-level rank of the mesh)
+    uint4* entries;             // [nseg][ent_cap] (ray's slot in the segment's mesh queue, top-level rank of the mesh, its root
+                                // node, its first triangle slot): everything the walker's fetch needs besides the ray
     uint32_t ent_cap;           // entries per segment
     int prim_bits;
 };
@@ -97,6 +95,12 @@ struct WalkAux {
 #define FW_WALK_CULL 2
 #endif
 
+// One deferred interior child on a lane's stack: (cull distance, node) in one 64-bit word — one local-memory access per
+// push / pop instead of two.
+FW_DEV unsigned long long stack_entry(float dist, int node) {
+    return ((unsigned long long)__float_as_uint(dist) << 32) | (uint32_t)node;
+}
+
 // Row byte offsets inside a wide node for a ray whose axes are permuted to (kx, ky, kz): near / far plane rows of each
 // permuted axis, one byte each (near plane = max row where the direction is negative, see wide_visit).
 FW_DEV void walk_rows(int kz, float3 inv_perm, uint32_t& near_pack, uint32_t& far_pack) {
@@ -110,7 +114,7 @@ FW_DEV void walk_rows(int kz, float3 inv_perm, uint32_t& near_pack, uint32_t& fa
 // (aabb.rs:30-50 arithmetic) and the cull are split into leaves (returned in l0..l3 for the caller to emit) and interior
 // nodes (nearest becomes `node`, the rest are pushed with their cull distance).
 FW_DEV void walk_visit(const float4* __restrict__ nodes, int& node, float3 o, float3 inv, uint32_t near_pack, uint32_t far_pack,
-                       float bound, int* stk_code, float* stk_te, int& sp, bool& l0, bool& l1, bool& l2, bool& l3, int4& cc) {
+                       float bound, unsigned long long* stk, int& sp, bool& l0, bool& l1, bool& l2, bool& l3, int4& cc) {
     const float tmin = 0.001f, tmax = 2e9f;   // render.rs:19
     const float4* n = &nodes[8 * node];
     const uintptr_t nb = reinterpret_cast<uintptr_t>(n);   // 128-byte aligned: row offsets are OR-ed in
@@ -148,9 +152,9 @@ FW_DEV void walk_visit(const float4* __restrict__ nodes, int& node, float3 o, fl
     cswap(t2, c2, t3, c3);
     cswap(t0, c0, t2, c2);   // (t0, c0) = nearest surviving interior child
     FW_WALK_CHECK(sp + 3 <= FW_WALK_STACK, "walk stack overflow sp=%d node=%d\n", sp, node);
-    if (t3 < miss) { stk_code[sp] = c3; stk_te[sp] = t3; ++sp; }
-    if (t2 < miss) { stk_code[sp] = c2; stk_te[sp] = t2; ++sp; }
-    if (t1 < miss) { stk_code[sp] = c1; stk_te[sp] = t1; ++sp; }
+    if (t3 < miss) stk[sp++] = stack_entry(t3, c3);
+    if (t2 < miss) stk[sp++] = stack_entry(t2, c2);
+    if (t1 < miss) stk[sp++] = stack_entry(t1, c1);
     node = (t0 < miss) ? c0 : -1;
 }
 

@@ -33,6 +33,7 @@ struct PathState {
     float4* atten;     // [FW_MAX_DEPTH][cap] attenuation chain, by path (see fold_radiance)
     float4* radiance;  // [cap] finished path radiance, by path
     uint32_t* counters;                // [FW_MAX_DEPTH + 2][FW_NUM_QUEUES][nseg] fill counts
+    uint32_t* poison;                  // [1] set by a shade kernel that wrote an attenuation which is not small and finite (per batch)
     uint32_t cap;
     uint32_t nseg, seg_cap;
 };

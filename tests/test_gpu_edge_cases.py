@@ -203,3 +203,23 @@ def test_linear_program_and_object_loop_kernels_agree(monkeypatch):
     assert len(nb.linear_program()) > 160
     nb.close()
     _compare(big, 48, 30, 2, False)
+
+
+def test_black_environment_miss_shortcut_is_exact(monkeypatch):
+    """part2_all and volume-like scenes have a black ColorEnv but procedural (noise) textures, so the miss kernel can not be
+    dropped statically; it returns at once unless a shade kernel flagged a non-finite / huge attenuation in the batch
+    (kernels_shade.cu miss_kernel<BLACK_ENV>).  The shortcut must not change a single bit of the sums."""
+    from conftest import native_scene, params_for
+    p = params_for("part2_all", 320, 180, 24, seed=6)
+    monkeypatch.setenv("FW_BLACK_ENV_SKIP", "0")
+    ns = native_scene("part2_all")
+    _, full, st_full = ns.render(p, want_rgb=False)
+    ns.close()
+    monkeypatch.setenv("FW_BLACK_ENV_SKIP", "1")
+    ns = native_scene("part2_all")
+    _, fast, st_fast = ns.render(p, want_rgb=False)
+    ns.close()
+    assert st_full["rays"] == st_fast["rays"]
+    assert np.array_equal(np.isnan(full), np.isnan(fast))
+    ok = ~np.isnan(full)
+    assert np.array_equal(full[ok], fast[ok])

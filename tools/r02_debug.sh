@@ -1,5 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -s -k "part2_final" 2>&1 | grep -E "part2_final|passed|failed|Error|assert" | head -20
-bash tools/r02_profile_all.sh
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest=$?; tail -3 gpurun_out/pytest_gpu.log
+W="suzanne teapot"
+echo "== default (small top)"; timeout 300 python tools/quick_bench.py $W 2>&1 | tail -2
+echo "== FW_SMALL_TOP=0"; FW_SMALL_TOP=0 timeout 300 python tools/quick_bench.py $W 2>&1 | tail -2
+timeout 300 python tools/r02_determinism.py teapot 1920 1080 16 | head -4
+FW_SMALL_TOP=0 timeout 300 python tools/r02_determinism.py teapot 1920 1080 16 | head -2
