@@ -56,6 +56,19 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise FireworkError(-100, f"{LIB_PATH} is missing: run `python -m firework_b200.build` "
                                       "(there is no CPU fallback)")
+        if "FW_NCCL_LIB" not in os.environ:
+            # fw_render_multi dlopens NCCL on first use; if PyTorch's bundled (newer) copy exists, use that one so that a
+            # later `import torch` in the same process finds the libnccl.so.2 it was built against (one library per SONAME)
+            try:
+                import importlib.util
+                spec = importlib.util.find_spec("nvidia.nccl")
+                for d in (spec.submodule_search_locations if spec else []):
+                    cand = os.path.join(d, "lib", "libnccl.so.2")
+                    if os.path.exists(cand):
+                        os.environ["FW_NCCL_LIB"] = cand
+                        break
+            except Exception:
+                pass
         L = C.CDLL(LIB_PATH)
         L.fw_last_error.restype = C.c_char_p
         L.fw_version.restype = C.c_char_p

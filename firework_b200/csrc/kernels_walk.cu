@@ -47,7 +47,13 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_WALK_MIN_BLOCKS) walk_mesh_kernel
     float bound0 = FW_FLT_MAX;                                      // FW_WALK_CULL == 0: the bound pass 1 left
     int node = -1, sp = 0;
     uint32_t slot_in = 0;
-    unsigned long long stk[FW_WALK_STACK];   // deferred interior children: (cull distance, node)
+#if FW_WALK_SMEM_STACK
+    __shared__ unsigned long long s_stk[FW_WALK_STACK_SMEM_DEPTH][FW_BLOCK];
+    const WalkStack stk{&s_stk[0][threadIdx.x]};
+#else
+    unsigned long long stk_local[FW_WALK_STACK];   // deferred interior children: (cull distance, node)
+    const WalkStack stk{stk_local};
+#endif
     int npairs = 0;
     bool input_left = true;
 
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_WALK_MIN_BLOCKS) walk_mesh_kernel
             if (node < 0) {
                 for (;;) {
                     if (sp == 0) { active = false; break; }
-                    const unsigned long long e = stk[--sp];
+                    const unsigned long long e = stk.at(--sp);
                     if (!(__uint_as_float((uint32_t)(e >> 32)) > bnd)) { node = (int)(uint32_t)e; break; }
                 }
             }

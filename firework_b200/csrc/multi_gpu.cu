@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <thread>
@@ -44,9 +45,13 @@ std::map<std::vector<int>, std::vector<ncclComm_t>> g_comms;   // communicators 
 
 bool load_nccl() {
     if (g_nccl.handle) return true;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    // FW_NCCL_LIB names the library to use.  A host that also loads another NCCL user later (PyTorch bundles its own, newer
+    // libnccl.so.2) must point this at THAT copy: the dynamic loader keeps one library per SONAME, so whichever is loaded
+    // first serves both (firework_b200/_native.py sets it when the nvidia-nccl wheel is installed).
+    const char* names[] = {getenv("FW_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
-        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (!n || !*n) continue;
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
         if (g_nccl.handle) break;
     }
     if (!g_nccl.handle) {

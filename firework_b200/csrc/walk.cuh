@@ -39,6 +39,10 @@ namespace fw {
 #define FW_WALK_CHECKS 0          // 1 = bounds checks with printf + trap in the walk kernels (debug builds)
 #endif
 #define FW_WALK_CHECK(cond, ...) do { if (FW_WALK_CHECKS && !(cond)) { printf(__VA_ARGS__); __trap(); } } while (0)
+#ifndef FW_WALK_SMEM_STACK
+#define FW_WALK_SMEM_STACK 0      // 1 = the walker's stack lives in shared memory ([level][thread], conflict-free) instead of local
+#endif
+constexpr int FW_WALK_STACK_SMEM_DEPTH = 32;   // 3 per wide level: covers mesh trees up to 9 wide levels (deeper ones: checked at flatten)
 constexpr int FW_WALK_STACK = 64;      // deferred interior children per lane (3 per wide level; checked at flatten)
 constexpr int FW_WALK_RING = 256;      // pair buffer (power of two): < 32 left over + at most 4 new per lane = 159 pending
 constexpr int FW_WALK_SLOTS = 32;      // entry slots per warp: one per lane
@@ -101,6 +105,12 @@ FW_DEV unsigned long long stack_entry(float dist, int node) {
     return ((unsigned long long)__float_as_uint(dist) << 32) | (uint32_t)node;
 }
 
+// Where a lane's stack lives: a private (local-memory) array, or one column of a block-wide shared-memory array.
+struct WalkStack {
+    unsigned long long* base;
+    FW_DEV unsigned long long& at(int i) const { return FW_WALK_SMEM_STACK ? base[(size_t)i * FW_BLOCK] : base[i]; }
+};
+
 // Row byte offsets inside a wide node for a ray whose axes are permuted to (kx, ky, kz): near / far plane rows of each
 // permuted axis, one byte each (near plane = max row where the direction is negative, see wide_visit).
 FW_DEV void walk_rows(int kz, float3 inv_perm, uint32_t& near_pack, uint32_t& far_pack) {
@@ -114,7 +124,7 @@ FW_DEV void walk_rows(int kz, float3 inv_perm, uint32_t& near_pack, uint32_t& fa
 // (aabb.rs:30-50 arithmetic) and the cull are split into leaves (returned in l0..l3 for the caller to emit) and interior
 // nodes (nearest becomes `node`, the rest are pushed with their cull distance).
 FW_DEV void walk_visit(const float4* __restrict__ nodes, int& node, float3 o, float3 inv, uint32_t near_pack, uint32_t far_pack,
-                       float bound, unsigned long long* stk, int& sp, bool& l0, bool& l1, bool& l2, bool& l3, int4& cc) {
+                       float bound, WalkStack stk, int& sp, bool& l0, bool& l1, bool& l2, bool& l3, int4& cc) {
     const float tmin = 0.001f, tmax = 2e9f;   // render.rs:19
     const float4* n = &nodes[8 * node];
     const uintptr_t nb = reinterpret_cast<uintptr_t>(n);   // 128-byte aligned: row offsets are OR-ed in
@@ -152,9 +162,9 @@ FW_DEV void walk_visit(const float4* __restrict__ nodes, int& node, float3 o, fl
     cswap(t2, c2, t3, c3);
     cswap(t0, c0, t2, c2);   // (t0, c0) = nearest surviving interior child
     FW_WALK_CHECK(sp + 3 <= FW_WALK_STACK, "walk stack overflow sp=%d node=%d\n", sp, node);
-    if (t3 < miss) stk[sp++] = stack_entry(t3, c3);
-    if (t2 < miss) stk[sp++] = stack_entry(t2, c2);
-    if (t1 < miss) stk[sp++] = stack_entry(t1, c1);
+    if (t3 < miss) stk.at(sp++) = stack_entry(t3, c3);
+    if (t2 < miss) stk.at(sp++) = stack_entry(t2, c2);
+    if (t1 < miss) stk.at(sp++) = stack_entry(t1, c1);
     node = (t0 < miss) ? c0 : -1;
 }
 

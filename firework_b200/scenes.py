@@ -17,7 +17,7 @@ import numpy as np
 
 from .api import (CameraSettings, CheckerTexture, Cone, ConstantTexture, Cylinder, DielectricMat, Disk,
                   EmissiveMat, F, HdrEnvironment, ImageTexture, LambertianMat, MetalMat, Rect3d, RenderObject,
-                  Renderer, Rotor3, Scene, SkyEnv, Sphere, TurbulenceTexture, Vec3, XYRect, XZRect, YZRect,
+                  Renderer, Rotor3, Scene, SkyEnv, Sphere, TriangleMesh, TurbulenceTexture, Vec3, XYRect, XZRect, YZRect,
                   to_radians)
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -145,6 +145,26 @@ def volume_scene() -> Scene:
     return scene
 
 
+# --- examples/heightmap.rs:11-52 (restated with the current API: Scene::add_mesh no longer exists) ---
+def heightmap_scene() -> Scene:
+    scene = Scene.new()
+    scene.set_environment(SkyEnv.default())
+    light = scene.add_material(EmissiveMat.with_color(Vec3.broadcast(8.0)))
+    scene.add_object(RenderObject.new(YZRect(0.0, 20.0, 0.0, 10.0, -3.0, light))
+                     .rotate(Rotor3.from_rotation_xz(-30.0)).position(0.0, 0.0, -10.0))
+    green = scene.add_material(LambertianMat.with_color(Vec3(0.0, 0.5, 0.3)))
+    verts, indicies, size = [], [], 20
+    for y in range(size):
+        for x in range(size):
+            height = np.cos(np.float32(x), dtype=np.float32) + np.sin(np.float32(y), dtype=np.float32)
+            verts.append((np.float32(x), np.float32(0.2) * np.float32(height), np.float32(y)))
+            if x != 0 and y != 0:
+                indicies += [(y - 1) * size + x - 1, y * size + x, (y - 1) * size + x]
+                indicies += [(y - 1) * size + x - 1, y * size + x - 1, y * size + x]
+    scene.add_object(RenderObject.new(TriangleMesh(verts, indicies, None, None, green)))
+    return scene
+
+
 # --- examples/part2_all.rs:13-80 (restated with Scene::add_volume) -------------------------------
 def final_scene(rand: SceneRng) -> Scene:
     scene = Scene.new()
@@ -230,6 +250,8 @@ CONFIGS = {
                      cite="examples/conics.rs:86-96"),
     "volume": Config("volume", "volume.yml", 960, 540, 2048, False, (0, 2, -10), (0, 0, 0),
                      cite="examples/volume_test.rs:62-70"),
+    "heightmap": Config("heightmap", "heightmap.yml", 960, 540, 32, True, (10, 6, -3), (10, 0, 10), vfov=40.0,
+                        cite="examples/heightmap.rs:54-66"),
     # the CLI's hard-coded view of any .yml (main.rs:28-38): BVH on, so Disk's degenerate bbox is live
     "conics_cli": Config("conics_cli", "conics.yml", 960, 540, 128, True, (0, 30, 50), (0, 0, 0), vfov=40.0,
                          cite="src/main.rs:28-38"),
@@ -246,6 +268,7 @@ def generate_scene_files(out_dir: str = SCENE_DIR) -> None:
         "earth.yml": earth_scene,
         "hdri_test.yml": hdri_test,
         "volume.yml": volume_scene,
+        "heightmap.yml": heightmap_scene,
         "part2_all.yml": lambda: final_scene(SceneRng(12345)),
     }
     for name, fn in gens.items():

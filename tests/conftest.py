@@ -15,7 +15,7 @@ from firework_b200.serde_yaml import loads  # noqa: E402
 
 ASSETS = os.path.join(SCENE_DIR, "assets")
 ALL_SCENES = ["random_spheres", "cornell_box", "suzanne", "teapot", "hdri_test", "earth", "part2_all", "conics",
-              "conics_cli", "volume"]
+              "conics_cli", "volume", "heightmap"]
 
 
 def pytest_configure(config):

@@ -2,7 +2,7 @@
 
 Run in the build container only (/root/reference is not on the GPU box).  These PNGs are renders of scenes that can be
 reproduced exactly — the serde dumps scenes/suzanne.yml, teapot.yml, conics.yml, and the deterministic scene
-constructors of examples/cornell_box.rs, earth.rs — with cameras fixed in the examples (unlike
+constructors of examples/cornell_box.rs, earth.rs, heightmap.rs — with cameras fixed in the examples (unlike
 random_spheres.png / part2_final.png, whose scenes come from an RNG crate that is not vendored).  The fixture holds
 their 8x8 box-filtered RGB means (noise-suppressed, 1/64 of the pixels); the GPU test renders the same scenes at the
 same resolution and compares box means (tests/test_gpu_parity.py).
@@ -15,7 +15,7 @@ REF = "/root/reference"
 # volume.png is left out: it was rendered with a camera / sphere size that the current examples/volume_test.rs no longer
 # has (the sphere fills twice the height it does with the example's camera), so it cannot be reproduced.
 FILES = {"suzanne": "suzanne.png", "teapot": "teapot.png", "cornell_box": "cornell_box.png", "conics": "conics.png",
-         "earth": "Earth.png"}
+         "earth": "Earth.png", "heightmap": "heightmap.png"}
 out = {}
 for name, fn in FILES.items():
     img = np.asarray(Image.open(os.path.join(REF, fn)).convert("RGB")).astype(np.float64)

@@ -20,8 +20,8 @@ REL = 1e-5  # the tolerance BASELINE.json states for t / normal / scatter
 #                suzanne  teapot  cornell_box  conics  earth
 # measured dB      51.0    45.2      44.2      49.5    43.3
 # mean abs /255    0.49    0.87      1.15      0.51    1.37
-PNG_PSNR_MIN = {"suzanne": 45.0, "teapot": 40.0, "cornell_box": 40.0, "conics": 44.0, "earth": 40.0}
-PNG_MEAN_ABS_MAX = {"suzanne": 1.5, "teapot": 2.0, "cornell_box": 2.5, "conics": 1.5, "earth": 2.5}
+PNG_PSNR_MIN = {"suzanne": 45.0, "teapot": 40.0, "cornell_box": 40.0, "conics": 44.0, "earth": 40.0, "heightmap": 43.0}
+PNG_MEAN_ABS_MAX = {"suzanne": 1.5, "teapot": 2.0, "cornell_box": 2.5, "conics": 1.5, "earth": 2.5, "heightmap": 1.5}
 
 
 def _rel(a, b, floor=1e-20):
@@ -425,11 +425,12 @@ def test_cli_checkpoint_resume(tmp_path, scenes):
 
 
 @pytest.mark.parametrize("name,spp,gamma", [("suzanne", 512, 2.2), ("teapot", 256, 2.2), ("cornell_box", 1000, 2.0),
-                                            ("conics", 256, 2.2), ("earth", 256, 2.2)])
+                                            ("conics", 256, 2.2), ("earth", 256, 2.2), ("heightmap", 256, 2.2)])
 def test_render_matches_the_references_committed_png(scenes, name, spp, gamma):
     """The only end-to-end artefacts the reference ships: renders of scenes that can be reproduced exactly —
     suzanne.png (examples/suzanne.rs:83-96, 960x540), teapot.png (examples/teapot.rs:96-109, 1920x1080) and conics.png
-    (examples/conics.rs:85-93) from the committed scenes/*.yml, cornell_box.png (examples/cornell_box.rs, 300x300;
+    (examples/conics.rs:85-93) from the committed scenes/*.yml, heightmap.png (examples/heightmap.rs, a procedural
+    height-field mesh), cornell_box.png (examples/cornell_box.rs, 300x300;
     rendered by an older revision whose output gamma was 2.0) and Earth.png (examples/earth.rs, 800x800).  The GPU render
     of the same scene at the same resolution must agree with them after an 8x8 box filter (their sample count and RNG
     differ, so the comparison is noise-limited): geometry, orientation, every shape's hit routine, flat vs interpolated
