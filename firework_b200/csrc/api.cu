@@ -591,6 +591,9 @@ int fw_set_batch_paths(fw_scene* sc, uint64_t paths) {
 // ----------------------------------------------------------------------------------------------------------
 // Segment geometry of a batch of `n` paths (wavefront.cuh "segmented queues"): enough segments to give every SM
 // several blocks, few enough that a segment still holds whole tiles.
+#ifndef FW_DEFAULT_BATCH_PATHS
+#define FW_DEFAULT_BATCH_PATHS (1ull << 27)
+#endif
 static constexpr uint32_t FW_SEG_PER_SM_MAX = 64;
 static void segment_geometry(const fw_scene* sc, size_t n, uint32_t* nseg, uint32_t* seg_cap) {
     size_t tiles = (n + FW_TILE - 1) / FW_TILE;
@@ -850,14 +853,36 @@ int fw::render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStream_t
     size_t npix = (size_t)p->width * p->height;
     // Paths in flight per batch.  Larger batches keep the deep, thinly populated bounces big enough to fill the
     // GPU and amortise the ~8 launches per bounce (measured: +6 % cornell, +18 % random_spheres, +34 % teapot
-    // from 4 Mi to 32 Mi paths); ~280 B of state per path -> 9 GB, small next to 180 GB of HBM.
-    size_t cap = sc->batch_paths ? sc->batch_paths : ((size_t)1 << 25);
+    // from 4 Mi to 32 Mi paths; part2_all at 4K another +6 % / +9 % at 64 Mi / 128 Mi); up to ~500 B of state per path
+    // (five material queues) -> 66 GB at 128 Mi paths, laid out for the 180 GB of HBM3e of a B200.
+    size_t cap = sc->batch_paths ? sc->batch_paths : ((size_t)FW_DEFAULT_BATCH_PATHS);
     if (const char* e = getenv("FW_BATCH_PATHS")) cap = std::max<size_t>(1024, strtoull(e, nullptr, 10));
     if (const char* e = getenv("FW_TWO_PASS")) sc->plan.two_pass = atoi(e) != 0;
     cap = std::min<size_t>(cap, npix * std::max<uint32_t>(p->sample_count, 1));
     cap = std::max<size_t>(cap, 32);
     int rc;
-    if ((rc = ensure_path_state(sc, cap)) != FW_OK) return rc;
+    if (cap > sc->ctx->ps_cap) {
+        // The context has to grow: keep the batch inside what the device can give (other scenes of this process hold
+        // contexts of their own).  Results do not depend on the batch split, only the speed does.
+        size_t queues = 1;   // + mesh queue
+        for (int k = 0; k < MAT_NUM_QUEUES; ++k) queues += (k != MAT_MISS && sc->mat_present[k]) ? 1 : 0;
+        const size_t per_path = 64 + 16 * FW_MAX_DEPTH + 16 + 16 + 48 * queues + (sc->plan.walk ? 8 + 16 * (size_t)sc->flat.n_top_meshes : 0);
+        size_t free_b = 0, total_b = 0;
+        FW_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const double budget = 0.8 * ((double)free_b + (double)sc->ctx->ps_cap * per_path);
+        while (cap > ((size_t)1 << 22) && (double)cap * per_path > budget) cap >>= 1;
+    }
+    for (;;) {   // ... and halve it if the allocation still fails
+        rc = ensure_path_state(sc, cap);
+        if (rc == FW_OK || cap <= ((size_t)1 << 20) || cudaPeekAtLastError() != cudaErrorMemoryAllocation) break;
+        cudaGetLastError();
+        free_path_state(sc->ctx->ps);
+        free_walk(sc->ctx);
+        sc->ctx->ps_cap = 0;
+        cap >>= 1;
+    }
+    if (rc != FW_OK) return rc;
+    cap = std::min<size_t>(cap, sc->ctx->ps_cap);
     RunTotals tot;
     size_t ev_next = 0;
     FW_CUDA(cudaMemsetAsync(sc->ctx->d_rays, 0, sizeof(unsigned long long), st));

@@ -87,11 +87,23 @@ FW_DEV void seg_close(const uint32_t* s_fill, const PathState& ps, uint32_t* cou
 }
 // Reserve one slot in queue `mine` of the segment for every lane with 0 <= mine < NQ: one shared-memory atomic per
 // warp per non-empty queue (warp ballot / popc compaction).  Returns the slot (global index); all 32 lanes must call.
+#ifndef FW_RESERVE_MATCH
+#define FW_RESERVE_MATCH 1   // 1 = group the lanes of a warp by queue with one match.any instead of one ballot round per queue
+#endif
 template <int NQ>
 FW_DEV uint32_t seg_reserve(uint32_t* s_fill, uint32_t seg_base, int mine) {
     unsigned lane = threadIdx.x & 31u;
     unsigned lt = (1u << lane) - 1u;
     uint32_t slot = 0;
+    if (FW_RESERVE_MATCH && NQ > 2) {
+        const unsigned grp = __match_any_sync(0xffffffffu, mine);   // the lanes that go to the same queue (or to none: mine < 0)
+        const int leader = __ffs(grp) - 1;
+        uint32_t base = 0;
+        if (mine >= 0 && (int)lane == leader) base = atomicAdd(&s_fill[mine], (uint32_t)__popc(grp));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (mine >= 0) slot = seg_base + base + __popc(grp & lt);
+        return slot;
+    }
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
         unsigned mask = __ballot_sync(0xffffffffu, mine == k);

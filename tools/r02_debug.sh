@@ -1,5 +1,6 @@
 #!/bin/bash
 set -u
-W="cornell_box random_spheres part2_all suzanne teapot"
-echo "== default"; timeout 300 python tools/quick_bench.py $W 2>&1 | tail -5
-for lib in firework_b200/variants/*.so; do echo "== $lib"; FW_LIB_PATH=$lib timeout 300 python tools/quick_bench.py $W 2>&1 | tail -5; done
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest=$?; tail -2 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1
+timeout 600 python bench.py --steps 3 --warmup 3 --per-config-steps 2 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo bench=$?; tail -c 300 gpurun_out/bench_quick.err
