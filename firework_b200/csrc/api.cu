@@ -1050,6 +1050,48 @@ int fw_first_hit(fw_scene* sc, int use_bvh, uint64_t seed, uint32_t n, const flo
     return FW_OK;
 }
 
+// The same query through the kernels a render launches (queues, segments, the scene's extend plan, finalize_hit).
+int fw_first_hit_wavefront(fw_scene* sc, int use_bvh, uint64_t seed, uint32_t n, const float* origins, const float* dirs,
+                           uint32_t sample, uint32_t bounce, int32_t* obj, int32_t* prim, int32_t* material, float* t, float* point,
+                           float* normal, float* uv) {
+    if (!sc || !origins || !dirs || !obj || !prim || !material || !t || !point || !normal || !uv)
+        return set_error(FW_ERR_ARG, "null argument");
+    if (!sc->committed) return set_error(FW_ERR_STATE, "scene not committed");
+    if (n == 0 || bounce > (uint32_t)FW_MAX_DEPTH) return set_error(FW_ERR_ARG, "need n > 0 and bounce <= 10");
+    FW_CUDA(cudaSetDevice(sc->device));
+    int rc = ensure_path_state(sc, std::max<size_t>(n, 32));
+    if (rc != FW_OK) return rc;
+    DevBuf dO, dD, oObj, oPrim, oMat, oT, oPt, oN, oUv;
+    TRY(dO.put(origins, (size_t)n * 12)); TRY(dD.put(dirs, (size_t)n * 12));
+    TRY(oObj.alloc((size_t)n * 4)); TRY(oPrim.alloc((size_t)n * 4)); TRY(oMat.alloc((size_t)n * 4)); TRY(oT.alloc((size_t)n * 4));
+    TRY(oPt.alloc((size_t)n * 12)); TRY(oN.alloc((size_t)n * 12)); TRY(oUv.alloc((size_t)n * 8));
+    FirstHitOut out{oObj.as<int>(), oPrim.as<int>(), oMat.as<int>(), oT.as<float>(), oPt.as<float>(), oN.as<float>(), oUv.as<float>(), nullptr};
+    cudaStream_t st = sc->ctx->stream;
+    PathState& ps = sc->ctx->ps;
+    segment_geometry(sc, n, &ps.nseg, &ps.seg_cap);
+    FW_CUDA(cudaMemsetAsync(ps.counters, 0, sizeof(uint32_t) * (FW_MAX_DEPTH + 2) * FW_NUM_QUEUES * (size_t)ps.nseg, st));
+    FW_CUDA(cudaMemsetAsync(ps.poison, 0, sizeof(uint32_t), st));
+    Batch b;   // ray i = path i = "pixel" i of a one-sample batch: RNG key (pixel i, sample, bounce)
+    b.pix0 = 0; b.npix = n; b.s0 = sample; b.ns = 1; b.width = n; b.height = 1;
+    b.npix_magic = n <= 1 ? 0xffffffffu : (uint32_t)((((uint64_t)1 << 32) + n - 1) / n);
+    const uint2 sd = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    launch_probe_fill(ps, n, dO.as<float>(), dD.as<float>(), bounce, st);
+    if (use_bvh && sc->plan.walk && sc->plan.two_pass) {
+        WalkAuxHost ax = sc->ctx->walk;
+        ax.ent_cap = ps.seg_cap * (uint32_t)std::max(1, sc->flat.n_top_meshes);
+        launch_extend_walk(sc->plan, sc->dscene, ps, b, sd, bounce, ax, st);
+    } else {
+        launch_extend(sc->plan, use_bvh != 0, sc->lin_prog, sc->dscene, ps, b, sd, bounce, st);
+    }
+    launch_probe_collect(sc->dscene, ps, bounce, out, st);
+    FW_CUDA(cudaGetLastError());
+    FW_CUDA(cudaStreamSynchronize(st));
+    TRY(oObj.get(obj, (size_t)n * 4)); TRY(oPrim.get(prim, (size_t)n * 4)); TRY(oMat.get(material, (size_t)n * 4));
+    TRY(oT.get(t, (size_t)n * 4)); TRY(oPt.get(point, (size_t)n * 12)); TRY(oN.get(normal, (size_t)n * 12));
+    TRY(oUv.get(uv, (size_t)n * 8));
+    return FW_OK;
+}
+
 int fw_scatter_step(fw_scene* sc, uint32_t n, const int32_t* material, const float* ray_o, const float* ray_d,
                     const float* hit_t, const float* hit_point, const float* hit_normal, const float* hit_uv,
                     const float* uniforms, uint32_t nu, float* emit, int32_t* scattered, float* atten, float* out_o,

@@ -146,6 +146,63 @@ __global__ void texture_sample_probe(DeviceScene S, int tex, uint32_t n, const f
     }
 }
 
+// ---- first-hit probe through the PRODUCTION extend kernels (fw_first_hit_wavefront) -----------------------------
+// probe_fill_kernel plays raygen's role with caller-supplied rays (ray i = path i, dealt to the segments tile by tile);
+// the scene's own extend kernels then run exactly as in a render; probe_collect_kernel reads every shade / miss queue
+// back and rebuilds the full hit record with finalize_hit, the routine the shade kernels use.
+__global__ void __launch_bounds__(FW_BLOCK) probe_fill_kernel(PathState ps, uint32_t n, const float* __restrict__ origins,
+                                                              const float* __restrict__ dirs, uint32_t bounce) {
+    const uint32_t seg = blockIdx.x;
+    const size_t base = (size_t)seg * ps.seg_cap;
+    uint32_t count = 0;
+    for (uint32_t e = threadIdx.x; e < ps.seg_cap; e += FW_BLOCK) {
+        uint32_t p = ((e / FW_TILE) * ps.nseg + seg) * FW_TILE + (e % FW_TILE);
+        if (p >= n) break;
+        ps.xo[bounce & 1][base + e] = make_float4(origins[3 * p], origins[3 * p + 1], origins[3 * p + 2], __uint_as_float(p));
+        ps.xd[bounce & 1][base + e] = make_float4(dirs[3 * p], dirs[3 * p + 1], dirs[3 * p + 2], 0.0f);
+        count = e + 1;
+    }
+    __shared__ uint32_t s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    if (count) atomicMax(&s_count, count);
+    __syncthreads();
+    if (threadIdx.x == 0) counter_row(ps, bounce, FW_Q_EXTEND)[seg] = s_count;
+}
+template <int K>
+FW_DEV void probe_collect_queue(const DeviceScene& S, const PathState& ps, uint32_t bounce, const FirstHitOut& out) {
+    const uint32_t total = counter_row(ps, bounce, K)[blockIdx.x];
+    const uint32_t base = blockIdx.x * ps.seg_cap;
+    for (uint32_t e = threadIdx.x; e < total; e += FW_BLOCK) {
+        if (K == MAT_MISS) {
+            const uint32_t i = __float_as_uint(ps.hq[K].d[base + e].w);
+            out.obj[i] = -1; out.prim[i] = 0; out.material[i] = -1; out.t[i] = 0.0f;
+            out.point[3 * i] = out.point[3 * i + 1] = out.point[3 * i + 2] = 0.0f;
+            out.normal[3 * i] = out.normal[3 * i + 1] = out.normal[3 * i + 2] = 0.0f;
+            out.uv[2 * i] = out.uv[2 * i + 1] = 0.0f;
+            continue;
+        }
+        const HitIn h = get_hit<K>(ps, base + e);
+        HitRecord rec;
+        finalize_hit(S, h.w, h.o, h.d, rec);
+        const uint32_t i = h.path;
+        out.obj[i] = rec.obj; out.prim[i] = rec.prim; out.material[i] = rec.material; out.t[i] = rec.t;
+        out.point[3 * i] = rec.point.x; out.point[3 * i + 1] = rec.point.y; out.point[3 * i + 2] = rec.point.z;
+        out.normal[3 * i] = rec.normal.x; out.normal[3 * i + 1] = rec.normal.y; out.normal[3 * i + 2] = rec.normal.z;
+        out.uv[2 * i] = rec.uv.x; out.uv[2 * i + 1] = rec.uv.y;
+    }
+}
+__global__ void __launch_bounds__(FW_BLOCK) probe_collect_kernel(DeviceScene S, PathState ps, uint32_t bounce, FirstHitOut out) {
+    probe_collect_queue<0>(S, ps, bounce, out); probe_collect_queue<1>(S, ps, bounce, out); probe_collect_queue<2>(S, ps, bounce, out);
+    probe_collect_queue<3>(S, ps, bounce, out); probe_collect_queue<4>(S, ps, bounce, out); probe_collect_queue<5>(S, ps, bounce, out);
+}
+void launch_probe_fill(const PathState& ps, uint32_t n, const float* origins, const float* dirs, uint32_t bounce, cudaStream_t st) {
+    probe_fill_kernel<<<ps.nseg, FW_BLOCK, 0, st>>>(ps, n, origins, dirs, bounce);
+}
+void launch_probe_collect(const DeviceScene& S, const PathState& ps, uint32_t bounce, const FirstHitOut& out, cudaStream_t st) {
+    probe_collect_kernel<<<ps.nseg, FW_BLOCK, 0, st>>>(S, ps, bounce, out);
+}
+
 // ---- roofline denominators (fw_measure_peaks) --------------------------------------------------------------
 __global__ void fp32_peak_kernel(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;

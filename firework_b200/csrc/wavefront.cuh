@@ -143,10 +143,26 @@ FW_DEV void put_hit(const PathState& ps, uint32_t slot, float3 o, float3 d, uint
     st_stream(&ps.hq[K].d[slot], make_float4(d.x, d.y, d.z, w.t));
     st_stream(&ps.hq[K].w[slot], make_float4(__int_as_float(w.obj), __int_as_float(w.h.prim), __int_as_float(material), __int_as_float(w.rank)));
 }
+#ifndef FW_ENQUEUE_INDEXED
+#define FW_ENQUEUE_INDEXED 1   // 1 = pick the queue's stream pointers with a (constant-bank) indexed load: one store sequence for the warp
+#endif
 template <int NQ>
 FW_DEV uint32_t enqueue_hit(const PathState& ps, uint32_t* s_fill, uint32_t seg_base, int mine, float3 o, float3 d, uint32_t path,
                             const Winner& w, int material) {
     uint32_t slot = seg_reserve<NQ>(s_fill, seg_base, mine);
+    if (FW_ENQUEUE_INDEXED) {
+        if (mine >= 0) {
+            const HitQueue q = ps.hq[mine];   // kernel-parameter space, indexed per lane
+            if (mine == MAT_MISS) {
+                st_stream(&q.d[slot], make_float4(d.x, d.y, d.z, __uint_as_float(path)));
+            } else {
+                st_stream(&q.o[slot], make_float4(o.x, o.y, o.z, __uint_as_float(path)));
+                st_stream(&q.d[slot], make_float4(d.x, d.y, d.z, w.t));
+                st_stream(&q.w[slot], make_float4(__int_as_float(w.obj), __int_as_float(w.h.prim), __int_as_float(material), __int_as_float(w.rank)));
+            }
+        }
+        return slot;
+    }
     switch (mine) {   // one arm per queue keeps the queue index a compile-time constant
         case 0: put_hit<0>(ps, slot, o, d, path, w, material); break;
         case 1: put_hit<1>(ps, slot, o, d, path, w, material); break;

@@ -185,6 +185,19 @@ class NativeScene:
         res["node_tests"], res["prim_tests"] = int(cnt[0]), int(cnt[1])
         return res
 
+    def first_hit_wavefront(self, origins, dirs, use_bvh: bool, seed=0, sample=0, bounce=0):
+        """The first-hit query through the kernels a render launches (fw_first_hit_wavefront); ray i is keyed as pixel i."""
+        o = np.ascontiguousarray(origins, np.float32)
+        d = np.ascontiguousarray(dirs, np.float32)
+        n = len(o)
+        res = {"obj": np.zeros(n, np.int32), "prim": np.zeros(n, np.int32), "material": np.zeros(n, np.int32),
+               "t": np.zeros(n, np.float32), "point": np.zeros((n, 3), np.float32),
+               "normal": np.zeros((n, 3), np.float32), "uv": np.zeros((n, 2), np.float32)}
+        N.check(N.lib().fw_first_hit_wavefront(self._h, 1 if use_bvh else 0, seed, n, N.ptr(o), N.ptr(d), int(sample), int(bounce),
+                                               N.ptr(res["obj"]), N.ptr(res["prim"]), N.ptr(res["material"]), N.ptr(res["t"]),
+                                               N.ptr(res["point"]), N.ptr(res["normal"]), N.ptr(res["uv"])))
+        return res
+
     def scatter_step(self, material, ray_o, ray_d, hit_t, hit_point, hit_normal, hit_uv, uniforms):
         n = len(material)
         material = np.ascontiguousarray(material, np.int32)

@@ -149,6 +149,13 @@ int fw_primary_rays(fw_scene* scene, const fw_params* params, uint32_t sample, u
 int fw_first_hit(fw_scene* scene, int use_bvh, uint64_t seed, uint32_t n, const float* origins, const float* dirs,
                  const uint32_t* pixel, const uint32_t* sample, const uint32_t* bounce, int32_t* obj, int32_t* prim,
                  int32_t* material, float* t, float* point, float* normal, float* uv, uint64_t counters[2]);
+/* fw_first_hit answers from a probe kernel that calls the traversal routines directly; fw_first_hit_wavefront pushes the
+ * same rays through the kernels a render launches — the segmented queues, the scene's own extend kernels (lock-step,
+ * linear program or the mesh walk) and finalize_hit — so the first-hit gate covers the production path.  Ray i is keyed
+ * as (pixel i, `sample`, `bounce`), bounce <= 10. */
+int fw_first_hit_wavefront(fw_scene* scene, int use_bvh, uint64_t seed, uint32_t n, const float* origins, const float* dirs,
+                           uint32_t sample, uint32_t bounce, int32_t* obj, int32_t* prim, int32_t* material, float* t,
+                           float* point, float* normal, float* uv);
 int fw_scatter_step(fw_scene* scene, uint32_t n, const int32_t* material, const float* ray_o, const float* ray_d,
                     const float* hit_t, const float* hit_point, const float* hit_normal, const float* hit_uv,
                     const float* uniforms, uint32_t nu, float* emit, int32_t* scattered, float* atten, float* out_o,

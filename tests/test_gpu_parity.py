@@ -102,6 +102,16 @@ def test_first_hit_gate(scenes, name):
         assert np.nanmax(np.abs(g["uv"][hit] - r["uv"][hit]), initial=0.0) <= 1e-5
         # the ordered traversal does no more work than the reference's exhaustive one
         assert g["node_tests"] <= r["aabb_tests"] and g["prim_tests"] <= r["prim_tests"]
+        # the same rays through the kernels a render launches (segmented queues, the scene's extend plan — lock-step BVH,
+        # linear program or pass 1 + mesh walk + classification —, finalize_hit): identical to the probe kernel bit for bit,
+        # hence to the oracle within the same tolerances
+        w = ns.first_hit_wavefront(o, d, cfg.use_bvh, seed=1234, sample=0, bounce=gen)
+        assert np.array_equal(w["obj"], r["obj"]) and np.array_equal(w["prim"], r["prim"]) and np.array_equal(w["material"], r["material"])
+        assert _rel(w["t"][hit], r["t"][hit]).max() <= REL
+        assert np.nanmax(np.abs(w["normal"][hit] - r["normal"][hit]) / nscale) <= REL
+        assert (np.abs(w["point"][hit] - r["point"][hit]) / pscale).max() <= REL
+        assert np.array_equal(np.isnan(w["uv"]), np.isnan(r["uv"]))
+        assert np.nanmax(np.abs(w["uv"][hit] - r["uv"][hit]), initial=0.0) <= 1e-5
 
 
 def test_first_hit_ties_and_coincident_geometry(scenes):
