@@ -187,11 +187,19 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass2_k
 template <bool NESTED, bool MESHES>
 __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_bvh_simple_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed,
                                                                                      uint32_t bounce) {
+#if FW_SMEM_TOP_NODES > 0
+    __shared__ __align__(128) float4 s_top[FW_SMEM_TOP_NODES * 8];
+    for (int i = threadIdx.x; i < FW_SMEM_TOP_NODES * 8; i += FW_BLOCK) s_top[i] = i < S.n_nodes * 8 ? __ldg(&S.nodes[i]) : make_float4(0, 0, 0, 0);
+    __syncthreads();
+    const float4* top = s_top;
+#else
+    const float4* top = nullptr;
+#endif
     FW_EXTEND_PROLOGUE(MAT_NUM_QUEUES)
         if (valid) {
             RngKey key{seed, 0u, 0u, bounce};
             batch_path(b, path, key.pixel, key.sample);
-            trace_unified<false, NESTED, MESHES>(S, o, d, key, w, nullptr);
+            trace_unified<false, NESTED, MESHES>(S, o, d, key, w, nullptr, top);
         }
     FW_EXTEND_EPILOGUE(MAT_NUM_QUEUES)
 }
