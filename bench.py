@@ -343,18 +343,32 @@ def main():
             s.close()
             return h2d, d2h
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        h2d = d2h = 0
-        for _ in range(e2e_steps):
-            a, b = e2e_step()
-            h2d, d2h = a, max(d2h, b)
-        barrier()
-        (e2e_s,) = allreduce([time.perf_counter() - t0], dist.ReduceOp.MAX if world > 1 else None)
-        out["e2e"] = {"value": float(npix) * spp * e2e_steps / e2e_s / 1e6, "unit": "Msamples/s",
+        def e2e_loop():
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            h2d = d2h = 0
+            for _ in range(e2e_steps):
+                a, b = e2e_step()
+                h2d, d2h = a, max(d2h, b)
+            barrier()
+            (e2e_s,) = allreduce([time.perf_counter() - t0], dist.ReduceOp.MAX if world > 1 else None)
+            return float(npix) * spp * e2e_steps / e2e_s / 1e6, h2d, d2h
+
+        e2e_v, h2d, d2h = e2e_loop()
+        out["e2e"] = {"value": e2e_v, "unit": "Msamples/s",
                       "h2d_bytes_per_step": int(h2d) + len(text_c), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                       "what": "YAML text + host texels -> fw_scene_from_yaml + commit (BVH build, H2D) + render -> host u8 image (D2H)"}
+        if assets_c:
+            # the texture store shares a resident array with a scene that is handed the same texels again (every step here);
+            # the same loop with the store off copies and uploads the texels every step
+            os.environ["FW_TEXTURE_CACHE"] = "0"
+            try:
+                cold_v, cold_h2d, _ = e2e_loop()
+            finally:
+                del os.environ["FW_TEXTURE_CACHE"]
+            out["e2e"]["texture_store"] = "on: texels already resident are shared, not uploaded (h2d_bytes_per_step counts what was copied)"
+            out["e2e"]["texture_store_off"] = {"value": cold_v, "h2d_bytes_per_step": int(cold_h2d) + len(text_c)}
         ns.close()
 
         # ---- rank 0: per-ray algorithmic work from the oracle's counters (+ the CPU port's speed at N = 1) -----
@@ -410,7 +424,8 @@ def main():
                 roof = r.get("roofline", {})
                 per_config[name] = {
                     "res_spp": f"{c.width}x{c.height}x{spp_c}", "value": r["value"], "mrays_per_s": r["mrays_per_s"],
-                    "ms_per_step": r["ms_per_step"], "e2e": r["e2e"]["value"], "roofline_frac": roof.get("frac"),
+                    "ms_per_step": r["ms_per_step"], "e2e": r["e2e"]["value"], "e2e_over_value": r["e2e"]["value"] / r["value"],
+                    "e2e_texture_store_off": (r["e2e"].get("texture_store_off") or {}).get("value"), "roofline_frac": roof.get("frac"),
                     "traffic": roof.get("traffic"), "lanes": (roof.get("issue_slots") or {}).get("lanes_of_32"),
                     "issue_useful_frac": (roof.get("issue_slots") or {}).get("useful_frac"),
                     "flops_per_ray": roof.get("flops_per_ray"), "extend_share_of_step": roof.get("extend_share_of_step"),
@@ -425,7 +440,8 @@ def main():
         roof = line.get("roofline", {})
         per_config[cfg.name] = {
             "res_spp": f"{width}x{height}x{spp_total}", "value": line["value"], "mrays_per_s": line["mrays_per_s"],
-            "ms_per_step": line["ms_per_step"], "e2e": line["e2e"]["value"], "roofline_frac": roof.get("frac"),
+            "ms_per_step": line["ms_per_step"], "e2e": line["e2e"]["value"], "e2e_over_value": line["e2e"]["value"] / line["value"],
+            "e2e_texture_store_off": (line["e2e"].get("texture_store_off") or {}).get("value"), "roofline_frac": roof.get("frac"),
             "traffic": roof.get("traffic"), "lanes": (roof.get("issue_slots") or {}).get("lanes_of_32"),
             "issue_useful_frac": (roof.get("issue_slots") or {}).get("useful_frac"), "flops_per_ray": roof.get("flops_per_ray"),
             "extend_share_of_step": roof.get("extend_share_of_step"), "cpu_port": (line.get("cpu_baseline") or {}).get("value"),

@@ -45,6 +45,7 @@ static HdrStaging* staging_acquire(size_t floats) {
 }
 static void staging_release(HdrStaging* h) {
     if (!h) return;
+    if (h->plain) { free(h->p); delete h; return; }
     std::lock_guard<std::mutex> lk(g_staging_mutex);
     h->in_use = false;
 }
@@ -74,6 +75,116 @@ static_assert(sizeof(ShapeRec) == 48 && sizeof(MeshRec) == 64 && sizeof(MatRec) 
 static std::mutex g_ctx_mutex;
 static std::vector<RenderCtx*> g_ctx_cache;
 
+// ----------------------------------------------------------------------------------------------------------
+// texture store: device-resident textures, process-wide, addressed by the content of the texels
+// ----------------------------------------------------------------------------------------------------------
+// A renderer that is handed the same environment map or image texture scene after scene (the usual case: one HDRI, many
+// frames) spends more time copying 100 MB of texels to pinned memory and over PCIe than it spends rendering a small
+// image.  fw_scene_set_image / fw_scene_set_hdr hash the caller's texels (128 bits, multi-threaded: ~1 ms per 100 MB);
+// when an array with that content is already resident the host copy is skipped, and a commit onto the same device shares
+// the array (textures are read-only).  FW_TEXTURE_CACHE=0 disables the lookup: every scene copies and uploads.
+static std::mutex g_tex_mutex;
+static std::vector<TexEntry*> g_tex;
+static uint64_t g_tex_tick = 0, g_tex_hits = 0, g_tex_fills = 0;
+static constexpr size_t kTexIdlePerDevice = 8;   // idle (unreferenced) arrays kept per device
+
+static bool tex_store_enabled() {
+    const char* e = getenv("FW_TEXTURE_CACHE");
+    return !(e && e[0] == '0');
+}
+static inline uint64_t mix64(uint64_t a, uint64_t b) {
+    __uint128_t m = (__uint128_t)a * b;
+    return (uint64_t)m ^ (uint64_t)(m >> 64);
+}
+// Two interleaved multiply-fold chains over 32-byte blocks (each 8-byte word enters exactly one multiplication);
+// not cryptographic — it guards against accidental reuse, the caller is trusted.
+static void hash_span(const unsigned char* p, size_t n, uint64_t out[2]) {
+    const uint64_t k0 = 0xa0761d6478bd642full, k1 = 0xe7037ed1a0b428dbull, k2 = 0x8ebc6af09c88c6e3ull, k3 = 0x589965cc75374cc3ull;
+    uint64_t s0 = k0 ^ n, s1 = k1 + n;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        uint64_t w[4];
+        memcpy(w, p + i, 32);
+        s0 = mix64(w[0] ^ k2, w[1] ^ s0);
+        s1 = mix64(w[2] ^ k3, w[3] ^ s1);
+    }
+    if (i < n) {
+        uint64_t w[4] = {0, 0, 0, 0};
+        memcpy(w, p + i, n - i);
+        s0 = mix64(w[0] ^ k2, w[1] ^ s0);
+        s1 = mix64(w[2] ^ k3, w[3] ^ s1);
+    }
+    out[0] = mix64(s0 ^ k1, s1 ^ k2);
+    out[1] = mix64(s1 ^ k0, s0 + k3);
+}
+static AssetKey hash_texels(const void* data, size_t bytes, uint32_t w, uint32_t h, int kind) {
+    AssetKey key;
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    const size_t piece = (size_t)1 << 20;
+    const size_t n_pieces = std::max<size_t>(1, (bytes + piece - 1) / piece);
+    std::vector<uint64_t> hs(2 * n_pieces);
+    unsigned want = 16u;
+    if (const char* e = getenv("FW_HASH_THREADS")) want = (unsigned)std::max(1, atoi(e));
+    unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::min(want, std::thread::hardware_concurrency())), n_pieces);
+    auto work = [&](unsigned t) {
+        for (size_t k = t; k < n_pieces; k += nt) hash_span(p + k * piece, std::min(piece, bytes - k * piece), &hs[2 * k]);
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    uint64_t a = 0x9e3779b97f4a7c15ull ^ w, b = 0xc2b2ae3d27d4eb4full ^ h ^ ((uint64_t)kind << 40);
+    for (size_t k = 0; k < n_pieces; ++k) {   // piece order matters
+        a = mix64(a ^ hs[2 * k], 0xd6e8feb86659fd93ull) + b;
+        b = mix64(b ^ hs[2 * k + 1], 0xa0761d6478bd642full) + a;
+    }
+    key.hashed = true;
+    key.hash[0] = a; key.hash[1] = b;
+    return key;
+}
+static void tex_destroy(TexEntry* e) {
+    cudaSetDevice(e->device);
+    if (e->tex) cudaDestroyTextureObject(e->tex);
+    if (e->arr) cudaFreeArray(e->arr);
+    if (e->ready) cudaEventDestroy(e->ready);
+    delete e;
+}
+// Resident entry with this content on any device (+1 reference), or null.
+static TexEntry* tex_find_any(const AssetKey& key, uint32_t w, uint32_t h, bool is_float) {
+    if (!key.hashed) return nullptr;
+    std::lock_guard<std::mutex> lk(g_tex_mutex);
+    for (TexEntry* e : g_tex)
+        if (e->hashed && e->hash[0] == key.hash[0] && e->hash[1] == key.hash[1] && e->w == w && e->h == h && e->is_float == is_float) {
+            ++e->refs;
+            return e;
+        }
+    return nullptr;
+}
+static void tex_unref(TexEntry* e) {
+    if (!e) return;
+    std::lock_guard<std::mutex> lk(g_tex_mutex);
+    --e->refs;
+    e->last_use = ++g_tex_tick;
+}
+// The device state of a scene is gone (its stream was synchronised): drop its references, keep a few idle arrays.
+static void tex_release(std::vector<TexEntry*>& used, int device) {
+    std::lock_guard<std::mutex> lk(g_tex_mutex);
+    for (TexEntry* e : used) { --e->refs; e->last_use = ++g_tex_tick; }
+    used.clear();
+    for (;;) {
+        size_t idle = 0;
+        size_t oldest = g_tex.size();
+        for (size_t i = 0; i < g_tex.size(); ++i)
+            if (g_tex[i]->device == device && g_tex[i]->refs == 0) {
+                ++idle;
+                if (oldest == g_tex.size() || g_tex[i]->last_use < g_tex[oldest]->last_use) oldest = i;
+            }
+        if (idle <= kTexIdlePerDevice) break;
+        tex_destroy(g_tex[oldest]);
+        g_tex.erase(g_tex.begin() + oldest);
+    }
+}
+
 
 static int arena_alloc(fw_scene* sc, size_t bytes, void** out) {
     RenderCtx* c = sc->ctx;
@@ -92,15 +203,51 @@ static int arena_alloc(fw_scene* sc, size_t bytes, void** out) {
     c->arena_used += bytes;
     return FW_OK;
 }
+// Small tables (a 500-object scene has seventeen of a few KB each) are gathered in a pinned staging buffer and go out as
+// one copy per contiguous arena range: each cudaMemcpyAsync from pageable memory costs 5-10 us of driver time.
+static constexpr size_t kStageCap = (size_t)4 << 20, kStageMaxTable = (size_t)256 << 10;
+static int stage_flush(RenderCtx* c) {
+    if (c->stage_len) {
+        size_t n = c->stage_len;
+        c->stage_len = 0;
+        FW_CUDA(cudaMemcpyAsync(c->stage_dst, c->h_stage + c->stage_begin, n, cudaMemcpyHostToDevice, c->stream));
+    }
+    return FW_OK;
+}
 template <class T>
 static int upload(fw_scene* sc, const std::vector<T>& host, const T** dev) {
-    size_t bytes = std::max<size_t>(host.size() * sizeof(T), 64);
+    RenderCtx* c = sc->ctx;
+    const size_t payload = host.size() * sizeof(T);
+    size_t bytes = std::max<size_t>(payload, 64);
     void* p = nullptr;
     int rc = arena_alloc(sc, bytes, &p);
     if (rc != FW_OK) return rc;
-    if (host.empty()) FW_CUDA(cudaMemsetAsync(p, 0, bytes, sc->ctx->stream));
-    else FW_CUDA(cudaMemcpyAsync(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, sc->ctx->stream));
-    sc->h2d_bytes += host.size() * sizeof(T);
+    const size_t padded = (bytes + 255) & ~(size_t)255;   // what arena_alloc reserved
+    if (!c->h_stage && !c->stage_failed) {
+        if (cudaMallocHost(&c->h_stage, kStageCap) != cudaSuccess) { cudaGetLastError(); c->h_stage = nullptr; c->stage_failed = true; }
+    }
+    if (c->h_stage && padded <= kStageMaxTable) {
+        if (c->stage_off + padded > kStageCap) {      // buffer full: wait for the copies that read it, start over
+            if ((rc = stage_flush(c)) != FW_OK) return rc;
+            FW_CUDA(cudaStreamSynchronize(c->stream));
+            c->stage_off = 0;
+        }
+        if (!(c->stage_len > 0 && c->stage_dst + c->stage_len == static_cast<char*>(p))) {
+            if ((rc = stage_flush(c)) != FW_OK) return rc;
+            c->stage_begin = c->stage_off;
+            c->stage_dst = static_cast<char*>(p);
+        }
+        char* h = c->h_stage + c->stage_off;
+        if (payload) memcpy(h, host.data(), payload);
+        if (padded > payload) memset(h + payload, 0, padded - payload);
+        c->stage_off += padded;
+        c->stage_len += padded;
+    } else {
+        if ((rc = stage_flush(c)) != FW_OK) return rc;
+        if (host.empty()) FW_CUDA(cudaMemsetAsync(p, 0, bytes, c->stream));
+        else FW_CUDA(cudaMemcpyAsync(p, host.data(), payload, cudaMemcpyHostToDevice, c->stream));
+    }
+    sc->h2d_bytes += payload;
     *dev = reinterpret_cast<const T*>(p);
     return FW_OK;
 }
@@ -125,9 +272,9 @@ static void destroy_ctx(RenderCtx* c) {
     free_walk(c);
     if (c->arena) cudaFree(c->arena);
     for (void* p : c->arena_retired) cudaFree(p);
-    for (auto& t : c->tex_cache) { if (t.tex) cudaDestroyTextureObject(t.tex); if (t.arr) cudaFreeArray(t.arr); }
     fr(c->d_sum); fr(c->d_rgb);
     if (c->h_rays) cudaFreeHost(c->h_rays);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_rays) cudaFree(c->d_rays);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -175,12 +322,7 @@ static void release_device(fw_scene* sc) {
         for (void* p : c->arena_retired) cudaFree(p);
         c->arena_retired.clear();
         c->arena_used = 0;                       // the next scene overwrites the tables
-        for (auto& t : c->tex_cache) t.in_use = false;
-        while (c->tex_cache.size() > 8) {        // keep the cache small: drop the oldest idle entries
-            if (c->tex_cache.front().tex) cudaDestroyTextureObject(c->tex_cache.front().tex);
-            if (c->tex_cache.front().arr) cudaFreeArray(c->tex_cache.front().arr);
-            c->tex_cache.erase(c->tex_cache.begin());
-        }
+        tex_release(sc->tex_used, sc->device);
         std::lock_guard<std::mutex> lk(g_ctx_mutex);
         c->in_use = false;  // back to the cache
         sc->ctx = nullptr;
@@ -265,6 +407,7 @@ void fw_scene_destroy(fw_scene* sc) {
     release_device(sc);   // synchronises the scene's stream: no upload from the staging buffers is still in flight
     if (!sc->asset_src)
         for (HdrStaging* h : sc->hdr_staging) staging_release(h);
+    for (TexEntry* e : sc->asset_held) tex_unref(e);
     delete sc;
 }
 
@@ -285,7 +428,13 @@ int fw_scene_set_image(fw_scene* sc, int i, uint32_t w, uint32_t h, const uint8_
         if (a.kind != 0) return set_error(FW_ERR_ARG, "asset is not an image");
         if (sc->committed) return set_error(FW_ERR_STATE, "scene already committed");
         a.w = w; a.h = h;
-        a.rgba.assign(rgba, rgba + (size_t)w * h * 4);
+        sc->asset_key.resize(sc->desc.assets.size());
+        sc->asset_held.resize(sc->desc.assets.size(), nullptr);
+        if (sc->asset_held[i]) { tex_unref(sc->asset_held[i]); sc->asset_held[i] = nullptr; }
+        sc->asset_key[i] = tex_store_enabled() ? hash_texels(rgba, (size_t)w * h * 4, w, h, 0) : AssetKey();
+        sc->asset_held[i] = tex_find_any(sc->asset_key[i], w, h, false);
+        if (sc->asset_held[i]) { a.rgba.clear(); }   // resident already: no host copy (host_texels() reads it back if ever needed)
+        else a.rgba.assign(rgba, rgba + (size_t)w * h * 4);
         a.provided = true;
         return FW_OK;
 });
@@ -301,52 +450,141 @@ int fw_scene_set_hdr(fw_scene* sc, int i, uint32_t w, uint32_t h, const float* r
         const size_t texels = (size_t)w * h;
         sc->hdr_staging.resize(sc->desc.assets.size(), nullptr);
         if (sc->hdr_staging[i]) { staging_release(sc->hdr_staging[i]); sc->hdr_staging[i] = nullptr; }
-        HdrStaging* st = staging_acquire(texels * 4);
-        if (st) {
-            expand_rgb_to_rgba(rgb, st->p, texels);
-            sc->hdr_staging[i] = st;
-            a.rgb.clear();
-        } else {
-            a.rgb.assign(rgb, rgb + texels * 3);
+        sc->asset_key.resize(sc->desc.assets.size());
+        sc->asset_held.resize(sc->desc.assets.size(), nullptr);
+        if (sc->asset_held[i]) { tex_unref(sc->asset_held[i]); sc->asset_held[i] = nullptr; }
+        sc->asset_key[i] = tex_store_enabled() ? hash_texels(rgb, texels * 3 * sizeof(float), w, h, 1) : AssetKey();
+        sc->asset_held[i] = tex_find_any(sc->asset_key[i], w, h, true);
+        a.rgb.clear();
+        if (!sc->asset_held[i]) {
+            HdrStaging* st = staging_acquire(texels * 4);
+            if (st) {
+                expand_rgb_to_rgba(rgb, st->p, texels);
+                sc->hdr_staging[i] = st;
+            } else {
+                a.rgb.assign(rgb, rgb + texels * 3);
+            }
         }
         a.provided = true;
         return FW_OK;
 });
 }
 
-static int make_texture(fw_scene* sc, const void* src, uint32_t w, uint32_t h, bool is_float, cudaTextureObject_t* out) {
-    RenderCtx* c = sc->ctx;
-    size_t row = (size_t)w * (is_float ? 16 : 4);
-    sc->h2d_bytes += row * h;
-    for (auto& t : c->tex_cache)
-        if (!t.in_use && t.w == w && t.h == h && t.is_float == is_float) {   // same geometry: refill the array
-            FW_CUDA(cudaMemcpy2DToArrayAsync(t.arr, 0, 0, src, row, row, h, cudaMemcpyHostToDevice, c->stream));
-            t.in_use = true;
-            *out = t.tex;
-            return FW_OK;
-        }
-    cudaChannelFormatDesc fmt = is_float ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
-    RenderCtx::CachedTex t;
-    FW_CUDA(cudaMallocArray(&t.arr, &fmt, w, h));
-    cudaError_t e = cudaMemcpy2DToArrayAsync(t.arr, 0, 0, src, row, row, h, cudaMemcpyHostToDevice, c->stream);
-    cudaResourceDesc rd;
-    memset(&rd, 0, sizeof(rd));
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = t.arr;
-    cudaTextureDesc td;
-    memset(&td, 0, sizeof(td));
-    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModePoint;  // nearest texel: texture.rs:296-309, hdri_test.rs:72-81
-    td.readMode = cudaReadModeElementType;
-    td.normalizedCoords = 0;
-    if (e == cudaSuccess) e = cudaCreateTextureObject(&t.tex, &rd, &td, nullptr);
-    if (e != cudaSuccess) {
-        cudaFreeArray(t.arr);
-        return set_error(FW_ERR_CUDA, std::string("texture upload: ") + cudaGetErrorString(e));
+// Host texels of asset i of `src` (RGBA8 in a.rgba, or RGBA fp32 in pinned staging): present unless set_* found the content
+// resident and skipped the copy — then they are read back from that array (a commit onto another device, a replica).
+static int host_texels(fw_scene* src, size_t i, const void** out) {
+    AssetDesc& a = src->desc.assets[i];
+    const size_t texels = (size_t)a.w * a.h;
+    if (a.kind == 0) {
+        if (a.rgba.size() == texels * 4) { *out = a.rgba.data(); return FW_OK; }
+    } else {
+        if (i < src->hdr_staging.size() && src->hdr_staging[i]) { *out = src->hdr_staging[i]->p; return FW_OK; }
     }
-    t.w = w; t.h = h; t.is_float = is_float; t.in_use = true;
-    c->tex_cache.push_back(t);
-    *out = t.tex;
+    TexEntry* e = i < src->asset_held.size() ? src->asset_held[i] : nullptr;
+    if (e) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(e->device);
+        cudaError_t err = cudaEventSynchronize(e->ready);
+        const size_t row = (size_t)a.w * (a.kind == 0 ? 4 : 16);
+        if (a.kind == 0) {
+            a.rgba.resize(texels * 4);
+            if (err == cudaSuccess) err = cudaMemcpy2DFromArray(a.rgba.data(), row, e->arr, 0, 0, row, a.h, cudaMemcpyDeviceToHost);
+            *out = a.rgba.data();
+        } else {
+            src->hdr_staging.resize(src->desc.assets.size(), nullptr);
+            HdrStaging* st = staging_acquire(texels * 4);
+            if (!st) { cudaSetDevice(cur); return set_error(FW_ERR_CUDA, "no pinned memory for the texel read-back"); }
+            src->hdr_staging[i] = st;
+            if (err == cudaSuccess) err = cudaMemcpy2DFromArray(st->p, row, e->arr, 0, 0, row, a.h, cudaMemcpyDeviceToHost);
+            *out = st->p;
+        }
+        cudaSetDevice(cur);
+        if (err != cudaSuccess) return set_error(FW_ERR_CUDA, std::string("texel read-back: ") + cudaGetErrorString(err));
+        return FW_OK;
+    }
+    if (a.kind == 1 && a.rgb.size() == texels * 3) {   // no pinned memory at set time: expand now
+        src->hdr_staging.resize(src->desc.assets.size(), nullptr);
+        HdrStaging* st = new HdrStaging();   // plain host memory, owned like a pooled buffer that is never reused
+        st->p = static_cast<float*>(malloc(texels * 4 * sizeof(float)));
+        if (!st->p) { delete st; return set_error(FW_ERR_SCENE, "out of host memory"); }
+        st->floats = texels * 4; st->in_use = true; st->plain = true;
+        expand_rgb_to_rgba(a.rgb.data(), st->p, texels);
+        src->hdr_staging[i] = st;
+        *out = st->p;
+        return FW_OK;
+    }
+    return set_error(FW_ERR_ASSET, "asset `" + a.path + "` has no texels");
+}
+
+// Texture object for asset i of `src` on sc's device: shared when the content is resident there, else uploaded into an idle
+// array of the same geometry or a new one.
+static int make_texture(fw_scene* sc, fw_scene* src, size_t i, cudaTextureObject_t* out) {
+    RenderCtx* c = sc->ctx;
+    const AssetDesc& a = src->desc.assets[i];
+    const bool is_float = a.kind == 1;
+    const uint32_t w = a.w, h = a.h;
+    const AssetKey key = i < src->asset_key.size() ? src->asset_key[i] : AssetKey();
+    TexEntry* e = nullptr;
+    if (key.hashed) {
+        std::lock_guard<std::mutex> lk(g_tex_mutex);
+        for (TexEntry* t : g_tex)
+            if (t->device == sc->device && t->hashed && t->hash[0] == key.hash[0] && t->hash[1] == key.hash[1] && t->w == w && t->h == h &&
+                t->is_float == is_float) { e = t; ++e->refs; ++g_tex_hits; break; }
+    }
+    if (e) {
+        sc->tex_used.push_back(e);
+        FW_CUDA(cudaStreamWaitEvent(c->stream, e->ready, 0));   // the fill may still be in flight on another scene's stream
+        *out = e->tex;
+        return FW_OK;
+    }
+    const void* texels = nullptr;
+    int rc = host_texels(src, i, &texels);
+    if (rc != FW_OK) return rc;
+    const size_t row = (size_t)w * (is_float ? 16 : 4);
+    {
+        std::lock_guard<std::mutex> lk(g_tex_mutex);
+        for (TexEntry* t : g_tex)
+            if (t->device == sc->device && t->refs == 0 && t->w == w && t->h == h && t->is_float == is_float) {   // same geometry: refill
+                e = t; ++e->refs; e->hashed = false;   // not addressable until the new content is in flight
+                break;
+            }
+        ++g_tex_fills;
+    }
+    if (!e) {
+        e = new TexEntry();
+        e->device = sc->device; e->w = w; e->h = h; e->is_float = is_float; e->refs = 1;
+        cudaChannelFormatDesc fmt = is_float ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
+        cudaError_t err = cudaMallocArray(&e->arr, &fmt, w, h);
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = e->arr;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;  // nearest texel: texture.rs:296-309, hdri_test.rs:72-81
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        if (err == cudaSuccess) err = cudaCreateTextureObject(&e->tex, &rd, &td, nullptr);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming);
+        if (err != cudaSuccess) {
+            tex_destroy(e);
+            return set_error(FW_ERR_CUDA, std::string("texture upload: ") + cudaGetErrorString(err));
+        }
+        std::lock_guard<std::mutex> lk(g_tex_mutex);
+        g_tex.push_back(e);
+    }
+    sc->tex_used.push_back(e);
+    FW_CUDA(cudaMemcpy2DToArrayAsync(e->arr, 0, 0, texels, row, row, h, cudaMemcpyHostToDevice, c->stream));
+    FW_CUDA(cudaEventRecord(e->ready, c->stream));
+    {
+        std::lock_guard<std::mutex> lk(g_tex_mutex);
+        e->hash[0] = key.hash[0]; e->hash[1] = key.hash[1];
+        e->hashed = key.hashed;
+    }
+    sc->h2d_bytes += row * h;
+    *out = e->tex;
     return FW_OK;
 }
 
@@ -401,10 +639,12 @@ int fw_scene_commit(fw_scene* sc, int device) {
 });
 }
 static int commit_uploads(fw_scene* sc) {
-    const fw_scene* src = sc->asset_src ? sc->asset_src : sc;
+    // texels are read (and, after a set-time cache hit, lazily materialised) through the scene the replica was cloned from
+    fw_scene* src = sc->asset_src ? const_cast<fw_scene*>(sc->asset_src) : sc;
     DeviceScene& D = sc->dscene;
     const HostFlat& F = sc->flat;
     int rc;
+    sc->ctx->stage_off = sc->ctx->stage_len = 0;   // the context was synchronised when its previous scene let go of it
 #define UP(field) if ((rc = upload(sc, F.field, &D.field)) != FW_OK) return rc
     UP(nodes); UP(top_leaves); UP(top_items); UP(leaf_posr); UP(leaf_meta); UP(obj_posr); UP(obj_meta); UP(obj_rot); UP(obj_irot); UP(shapes); UP(meshes);
     UP(tri_verts); UP(tri_perm); UP(tri_normals); UP(tri_uvs); UP(mats); UP(texs);
@@ -416,25 +656,18 @@ static int commit_uploads(fw_scene* sc) {
     for (int k = 0; k < 3; ++k) { D.env.a[k] = sc->desc.env_a[k]; D.env.b[k] = sc->desc.env_b[k]; }
     for (size_t i = 0; i < src->desc.assets.size(); ++i) {
         const AssetDesc& a = src->desc.assets[i];
+        // host texels (a.rgba / the pinned staging copy) stay with the scene until fw_scene_destroy: the upload is
+        // asynchronous, and fw_render_multi replicates the scene onto other devices from them
+        cudaTextureObject_t t;
+        if ((rc = make_texture(sc, src, i, &t)) != FW_OK) return rc;
         if (a.kind == 0) {
-            if ((rc = make_texture(sc, a.rgba.data(), a.w, a.h, false, &images[i].tex)) != FW_OK) return rc;
-            images[i].w = a.w; images[i].h = a.h;
-        } else {
-            cudaTextureObject_t t;
-            // the pinned staging copy stays with the scene until fw_scene_destroy: the upload below is asynchronous, and
-            // fw_render_multi replicates the scene onto other devices from it
-            HdrStaging* hs = i < src->hdr_staging.size() ? src->hdr_staging[i] : nullptr;
-            if (hs) {
-                if ((rc = make_texture(sc, hs->p, a.w, a.h, true, &t)) != FW_OK) return rc;
-            } else {
-                std::vector<float> rgba((size_t)a.w * a.h * 4);
-                expand_rgb_to_rgba(a.rgb.data(), rgba.data(), (size_t)a.w * a.h);
-                if ((rc = make_texture(sc, rgba.data(), a.w, a.h, true, &t)) != FW_OK) return rc;
-            }
-            if ((int)i == sc->desc.env_asset) { D.env.tex = t; D.env.w = a.w; D.env.h = a.h; }
+            images[i].tex = t; images[i].w = a.w; images[i].h = a.h;
+        } else if ((int)i == sc->desc.env_asset) {
+            D.env.tex = t; D.env.w = a.w; D.env.h = a.h;
         }
     }
     if ((rc = upload(sc, images, &D.images)) != FW_OK) return rc;
+    if ((rc = stage_flush(sc->ctx)) != FW_OK) return rc;
     D.n_objects = (int)sc->desc.objects.size();
     D.n_nodes = (int)(F.nodes.size() / 8);
     D.n_tris = (int)(F.tri_verts.size() / 3);
@@ -571,6 +804,22 @@ int fw_release_cached_memory(void) {
         for (HdrStaging* h : g_staging)
             if (!h->in_use && h->p) { cudaFreeHost(h->p); h->p = nullptr; h->floats = 0; }
     }
+    {
+        std::lock_guard<std::mutex> lk3(g_tex_mutex);
+        std::vector<TexEntry*> keep_tex;
+        for (TexEntry* e : g_tex) {
+            if (e->refs > 0) keep_tex.push_back(e);
+            else tex_destroy(e);
+        }
+        g_tex.swap(keep_tex);
+    }
+    return FW_OK;
+}
+int fw_texture_store_stats(uint64_t out[4]) {
+    if (!out) return set_error(FW_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> lk(g_tex_mutex);
+    out[0] = g_tex_hits; out[1] = g_tex_fills; out[2] = g_tex.size(); out[3] = 0;
+    for (TexEntry* e : g_tex) out[3] += (uint64_t)e->w * e->h * (e->is_float ? 16 : 4);
     return FW_OK;
 }
 int fw_set_profiling(fw_scene* sc, int enabled) {

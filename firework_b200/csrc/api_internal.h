@@ -27,6 +27,7 @@ struct HdrStaging {
     float* p = nullptr;
     size_t floats = 0;
     bool in_use = false;
+    bool plain = false;   // malloc'ed fallback (no pinned memory): freed on release instead of pooled
 };
 
 // Render-time device state (path-state streams, sum / image buffers, stream, events).  It is independent of the
@@ -54,14 +55,31 @@ struct RenderCtx {
     char* arena = nullptr;
     size_t arena_cap = 0, arena_used = 0;
     std::vector<void*> arena_retired;   // outgrown slabs, freed when the scene that may still use them is released
-    // Texture arrays are kept for the next scene that needs the same geometry (the usual case: the same scene again).
-    struct CachedTex {
-        cudaArray_t arr = nullptr;
-        cudaTextureObject_t tex = 0;
-        uint32_t w = 0, h = 0;
-        bool is_float = false, in_use = false;
-    };
-    std::vector<CachedTex> tex_cache;
+    // pinned staging for the small scene tables (api.cu upload): one H2D copy per contiguous arena range
+    char* h_stage = nullptr;
+    bool stage_failed = false;
+    size_t stage_off = 0, stage_begin = 0, stage_len = 0;
+    char* stage_dst = nullptr;
+};
+
+// Device-resident texture, process-wide and content-addressed (api.cu "texture store"): texels handed to
+// fw_scene_set_image / fw_scene_set_hdr are hashed, and a scene whose texels are already resident on its device shares
+// the array (read-only) instead of copying and uploading them again.
+struct TexEntry {
+    int device = 0;
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+    cudaEvent_t ready = nullptr;   // recorded on the filling stream after the upload
+    uint32_t w = 0, h = 0;
+    bool is_float = false;
+    bool hashed = false;           // false: filled with the store disabled (never shared by content)
+    uint64_t hash[2] = {0, 0};
+    int refs = 0;                  // scenes holding it: matched at set time and / or committed with it
+    uint64_t last_use = 0;
+};
+struct AssetKey {
+    bool hashed = false;
+    uint64_t hash[2] = {0, 0};
 };
 
 struct fw_scene {
@@ -78,6 +96,9 @@ struct fw_scene {
     bool lin_prog_ok = false;  // the scene's program fits FW_LIN_MAX_WORDS (else: object-loop kernels)
     bool mat_present[MAT_NUM_QUEUES] = {false, false, false, false, false, false};
     std::vector<HdrStaging*> hdr_staging;   // per asset: pinned RGBA copy of an HDR map (set_hdr .. commit)
+    std::vector<AssetKey> asset_key;        // per asset: content hash of the texels handed in
+    std::vector<TexEntry*> asset_held;      // per asset: resident copy matched at set time (the host copy was skipped)
+    std::vector<TexEntry*> tex_used;        // entries the committed device scene reads (released with the device state)
     bool miss_is_zero = false;  // every escaping path contributes exactly 0: the miss kernel is not launched
     bool env_black = false;     // black ColorEnv: the miss kernel only has work in a batch some attenuation poisoned
     RenderCtx* ctx = nullptr;  // render-time state, borrowed from the per-device cache at commit

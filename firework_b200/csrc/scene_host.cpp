@@ -1,5 +1,7 @@
 #include "scene_host.h"
 
+#include <charconv>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -35,7 +37,15 @@ struct Loader {
     bool as_f32(const Node* n, float& out) {
         if (!n) return false;
         if (n->kind != Node::SCALAR) return fail(n, "expected a number");
-        const std::string& s = n->scalar;
+        const std::string_view v = n->scalar;
+        // the common case — a plain decimal — through from_chars (no locale, no copy); everything it does not take
+        // whole (".inf", "+1", hex, ...) through the YAML spellings and strtod as before.  Both round correctly.
+        {
+            double d;
+            auto r = std::from_chars(v.data(), v.data() + v.size(), d);
+            if (r.ec == std::errc() && r.ptr == v.data() + v.size()) { out = (float)d; return true; }
+        }
+        const std::string s(v);
         if (s == ".nan" || s == ".NaN") { out = NAN; return true; }
         if (s == ".inf" || s == "+.inf") { out = INFINITY; return true; }
         if (s == "-.inf") { out = -INFINITY; return true; }
@@ -48,7 +58,13 @@ struct Loader {
     bool as_u64(const Node* n, uint64_t& out) {
         if (!n) return false;
         if (n->kind != Node::SCALAR) return fail(n, "expected an integer");
-        const std::string& s = n->scalar;
+        const std::string_view sv = n->scalar;
+        {
+            unsigned long long v;
+            auto r = std::from_chars(sv.data(), sv.data() + sv.size(), v, 10);
+            if (r.ec == std::errc() && r.ptr == sv.data() + sv.size()) { out = v; return true; }
+        }
+        const std::string s(sv);
         char* end = nullptr;
         if (!s.empty() && s[0] == '-') return fail(n, "expected a non-negative integer, got `" + s + "`");
         unsigned long long v = strtoull(s.c_str(), &end, 10);
@@ -74,7 +90,7 @@ struct Loader {
     bool as_str(const Node* n, std::string& out) {
         if (!n) return false;
         if (n->kind != Node::SCALAR) return fail(n, "expected a string");
-        out = n->scalar;
+        out = std::string(n->scalar);
         return true;
     }
     bool as_v3(const Node* n, float out[3]) {
@@ -206,14 +222,14 @@ struct Loader {
             if (!faces) return -1;
             if (faces->kind != Node::SEQ && !faces->is_null()) { fail(faces, "expected a list of faces"); return -1; }
             std::vector<ShapeRec> fr;
-            for (const Node& f : faces->seq) {
+            for (const Node& f : faces->children) {
                 // enum Rect { XY(..), XZ(..), YZ(..) } — externally tagged: {XY: {...}}
-                if (f.kind != Node::MAP || f.map.size() != 1) { fail(&f, "expected {XY|XZ|YZ: rect}"); return -1; }
-                int plane = plane_of(f.map[0].first);
-                if (plane < 0) { fail(&f, "unknown Rect variant `" + f.map[0].first + "`"); return -1; }
+                if (f.kind != Node::MAP || f.children.size() != 1) { fail(&f, "expected {XY|XZ|YZ: rect}"); return -1; }
+                int plane = plane_of(std::string(f.children[0].key));
+                if (plane < 0) { fail(&f, "unknown Rect variant `" + std::string(f.children[0].key) + "`"); return -1; }
                 ShapeRec r;
-                if (f.map[0].second.kind != Node::MAP) { fail(&f, "expected rect fields"); return -1; }
-                if (!rect_fields(f.map[0].second, plane, r)) return -1;
+                if (f.children[0].kind != Node::MAP) { fail(&f, "expected rect fields"); return -1; }
+                if (!rect_fields(f.children[0], plane, r)) return -1;
                 fr.push_back(r);
             }
             s.i0 = (int)sc.shapes.size();
@@ -227,14 +243,14 @@ struct Loader {
             const Node* verts = req(n, "verts");
             if (!idx || !verts) return -1;
             if (idx->kind != Node::SEQ || verts->kind != Node::SEQ) { fail(&n, "mesh needs indicies and verts lists"); return -1; }
-            m.indicies.reserve(idx->seq.size());
-            for (const Node& i : idx->seq) {
+            m.indicies.reserve(idx->children.size());
+            for (const Node& i : idx->children) {
                 uint64_t v;
                 if (!as_u64(&i, v)) return -1;
                 m.indicies.push_back((uint32_t)v);
             }
-            m.verts.reserve(verts->seq.size());
-            for (const Node& v : verts->seq) {
+            m.verts.reserve(verts->children.size());
+            for (const Node& v : verts->children) {
                 float p[3];
                 if (!as_v3(&v, p)) return -1;
                 m.verts.push_back(V3{p[0], p[1], p[2]});
@@ -242,7 +258,7 @@ struct Loader {
             const Node* nn = n.get("normals");
             if (nn && nn->kind == Node::SEQ) {
                 m.has_normals = true;
-                for (const Node& v : nn->seq) {
+                for (const Node& v : nn->children) {
                     float p[3];
                     if (!as_v3(&v, p)) return -1;
                     m.normals.push_back(V3{p[0], p[1], p[2]});
@@ -252,7 +268,7 @@ struct Loader {
             const Node* un = n.get("uvs");
             if (un && un->kind == Node::SEQ) {
                 m.has_uvs = true;
-                for (const Node& v : un->seq) {
+                for (const Node& v : un->children) {
                     float p[2];
                     if (!as_v2(&v, p)) return -1;
                     m.uvs.push_back(p[0]);
@@ -324,10 +340,10 @@ struct Loader {
         const Node* env = req(root, "environment");
         if (!mats || !objs || !env) return false;
         if (mats->kind == Node::SEQ)
-            for (const Node& m : mats->seq)
+            for (const Node& m : mats->children)
                 if (!material(m)) return false;
         if (objs->kind == Node::SEQ)
-            for (const Node& o : objs->seq)
+            for (const Node& o : objs->children)
                 if (!object(o)) return false;
         // validate material indices (the reference would panic on use: scene.rs:86)
         for (const ShapeRec& s : sc.shapes)
@@ -492,6 +508,61 @@ bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& er
             return a == 0 ? 0.5 * ((double)x.mn.x + x.mx.x) : a == 1 ? 0.5 * ((double)x.mn.y + x.mx.y) : 0.5 * ((double)x.mn.z + x.mx.z);
         };
         constexpr int kMaxDepth = 22;   // binary levels below the root: keeps the traversal stack within FW_STACK
+        // Full-sweep SAH over the leaves, per node: order by centre along x, then (stably) y, then z; for every axis sweep
+        // the split position.  All per-node state lives in slices [lo, lo + n) of buffers sized once (a node is done with
+        // its slice before its children use theirs), and the leaf centres / areas are computed once: scene builds are on
+        // the end-to-end path of every render, and the per-node vectors + std::stable_sort's temporary
+        // buffer were most of fw_scene_commit for a 500-object scene.
+        const int nl = (int)leaves.size();
+        const int n_bn = (int)b.nodes.size();
+        std::vector<double> ctr[3];
+        for (int a = 0; a < 3; ++a) {
+            ctr[a].resize(n_bn);
+            for (int id : leaves) {
+                double c = center(id, a);
+                ctr[a][id] = c == c ? c : INFINITY;   // NaN centre (unbounded box): any consistent place will do
+            }
+        }
+        std::vector<int> ord[3];
+        for (int a = 0; a < 3; ++a) ord[a].resize(nl);
+        std::vector<double> right_area(nl);
+        std::vector<int> merge_tmp(nl);
+        auto sort_by = [&](int* v, int n, const std::vector<double>& key) {   // stable, ascending
+            if (n <= 32) {
+                for (int i = 1; i < n; ++i) {
+                    int x = v[i];
+                    double kx = key[x];
+                    int j = i;
+                    while (j > 0 && kx < key[v[j - 1]]) { v[j] = v[j - 1]; --j; }
+                    v[j] = x;
+                }
+                return;
+            }
+            // bottom-up merge sort over runs of 16 sorted by insertion
+            for (int r = 0; r < n; r += 16) {
+                int e = std::min(n, r + 16);
+                for (int i = r + 1; i < e; ++i) {
+                    int x = v[i];
+                    double kx = key[x];
+                    int j = i;
+                    while (j > r && kx < key[v[j - 1]]) { v[j] = v[j - 1]; --j; }
+                    v[j] = x;
+                }
+            }
+            int* src = v;
+            int* dst = merge_tmp.data();
+            for (int w = 16; w < n; w *= 2) {
+                for (int r = 0; r < n; r += 2 * w) {
+                    int m = std::min(n, r + w), e = std::min(n, r + 2 * w);
+                    int i = r, j = m, o = r;
+                    while (i < m && j < e) dst[o++] = key[src[j]] < key[src[i]] ? src[j++] : src[i++];
+                    while (i < m) dst[o++] = src[i++];
+                    while (j < e) dst[o++] = src[j++];
+                }
+                std::swap(src, dst);
+            }
+            if (src != v) std::copy(src, src + n, v);
+        };
         std::function<int(int, int, int)> sah = [&](int lo, int n, int depth) -> int {
             if (n == 1) return leaves[lo];
             int best_axis = -1, best_k = n / 2;
@@ -499,28 +570,30 @@ bool build_bvh(const std::vector<Box>& item_boxes, FlatBVH& out, std::string& er
             int levels_needed = 0;
             while ((1 << levels_needed) < n) ++levels_needed;
             const bool balanced = depth + levels_needed >= kMaxDepth;
-            std::vector<int> tmp(leaves.begin() + lo, leaves.begin() + lo + n), best_order;
-            std::vector<double> right_area(n);
+            int items_total = 0;
+            for (int i = 0; i < n; ++i) items_total += b.nodes[leaves[lo + i]].count;
             for (int a = 0; a < 3; ++a) {
-                std::stable_sort(tmp.begin(), tmp.end(), [&](int p, int q) { return center(p, a) < center(q, a); });
+                int* tmp = ord[a].data() + lo;
+                const int* from = a == 0 ? leaves.data() + lo : ord[a - 1].data() + lo;
+                std::copy(from, from + n, tmp);
+                sort_by(tmp, n, ctr[a]);
                 Box acc = b.nodes[tmp[n - 1]].box;
                 for (int i = n - 1; i > 0; --i) {
                     acc = box_expand(acc, b.nodes[tmp[i]].box);
-                    right_area[i] = area(acc);
+                    right_area[lo + i] = area(acc);
                 }
                 acc = b.nodes[tmp[0]].box;
-                int items_left = 0, items_total = 0;
-                for (int i = 0; i < n; ++i) items_total += b.nodes[tmp[i]].count;
+                int items_left = 0;
                 for (int k = 1; k < n; ++k) {   // left = tmp[0..k), right = tmp[k..n)
                     acc = box_expand(acc, b.nodes[tmp[k - 1]].box);
                     items_left += b.nodes[tmp[k - 1]].count;
                     if (balanced && k != n / 2) continue;
-                    double cost = area(acc) * items_left + right_area[k] * (items_total - items_left);
-                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_k = k; best_order = tmp; }
+                    double cost = area(acc) * items_left + right_area[lo + k] * (items_total - items_left);
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_k = k; }
                 }
             }
-            if (best_axis < 0) { best_order = tmp; best_k = n / 2; }   // non-finite areas: any split is valid
-            std::copy(best_order.begin(), best_order.end(), leaves.begin() + lo);
+            if (best_axis < 0) { best_axis = 2; best_k = n / 2; }   // non-finite areas: any split is valid
+            std::copy(ord[best_axis].begin() + lo, ord[best_axis].begin() + lo + n, leaves.begin() + lo);
             int l = sah(lo, best_k, depth + 1);
             int r = sah(lo + best_k, n - best_k, depth + 1);
             int id = (int)b.nodes.size();

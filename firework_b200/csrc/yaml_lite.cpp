@@ -4,10 +4,14 @@
 
 namespace fwyaml {
 
-const Node* Node::get(const char* key) const {
+const Node* Node::get(std::string_view k) const {
     if (kind != MAP) return nullptr;
-    for (const auto& kv : map)
-        if (kv.first == key) return &kv.second;
+    // serde writes the fields in declaration order and the loader asks for them in that order: look first at the entry
+    // after the previous answer.  (A mapping with a repeated key — which serde rejects — answers with one of them.)
+    const size_t n = children.size();
+    if (hint < n && children[hint].key == k) return &children[hint++];
+    for (size_t i = 0; i < n; ++i)
+        if (children[i].key == k) { hint = (unsigned)i + 1; return &children[i]; }
     return nullptr;
 }
 
@@ -24,6 +28,13 @@ struct Parser {
     std::vector<Line> lines;
     size_t pos = 0;
     std::string err;
+    std::deque<std::string>* pool = nullptr;   // created on first use, handed to the root
+    std::string_view keep(std::string&& s) {
+        if (!pool) pool = new std::deque<std::string>();
+        pool->push_back(std::move(s));
+        return pool->back();
+    }
+    ~Parser() { delete pool; }
 
     bool fail(int line, const std::string& msg) {
         if (err.empty()) err = "line " + std::to_string(line) + ": " + msg;
@@ -34,7 +45,23 @@ struct Parser {
     static void skip_ws(const char*& p, const char* e) {
         while (p < e && (*p == ' ' || *p == '\t')) ++p;
     }
-    bool parse_quoted(const char*& p, const char* e, std::string& out, int line) {
+    // Quoted scalar at p: a view of the text between the quotes when nothing needs unescaping, else of a pooled copy.
+    bool parse_quoted(const char*& p, const char* e, std::string_view& view, int line) {
+        const char q = *p;
+        const char* b = p + 1;
+        const char* c = b;
+        while (c < e && *c != q && !(q == '"' && *c == '\\')) ++c;
+        if (c < e && *c == q && !(q == '\'' && c + 1 < e && c[1] == '\'')) {
+            view = std::string_view(b, (size_t)(c - b));
+            p = c + 1;
+            return true;
+        }
+        std::string out;
+        if (!unescape_quoted(p, e, out, line)) return false;
+        view = keep(std::move(out));
+        return true;
+    }
+    bool unescape_quoted(const char*& p, const char* e, std::string& out, int line) {
         char q = *p++;
         out.clear();
         while (p < e) {
@@ -59,12 +86,12 @@ struct Parser {
     }
     static void set_plain(Node& n, const char* b, const char* e) {
         while (e > b && (e[-1] == ' ' || e[-1] == '\t')) --e;
-        std::string s(b, e);
+        std::string_view s(b, (size_t)(e - b));
         if (s.empty() || s == "~" || s == "null" || s == "Null" || s == "NULL") {
             n.kind = Node::NUL;
         } else {
             n.kind = Node::SCALAR;
-            n.scalar = std::move(s);
+            n.scalar = s;
         }
     }
     // value inside a flow collection or as a whole line; `stops` = extra terminators in flow context
@@ -83,7 +110,7 @@ struct Parser {
             for (;;) {
                 Node item;
                 if (!parse_flow_value(p, e, item, line, true, depth + 1)) return false;
-                n.seq.push_back(std::move(item));
+                n.children.push_back(std::move(item));
                 skip_ws(p, e);
                 if (p < e && *p == ',') { ++p; continue; }
                 if (p < e && *p == ']') { ++p; return true; }
@@ -97,7 +124,7 @@ struct Parser {
             if (p < e && *p == '}') { ++p; return true; }
             for (;;) {
                 skip_ws(p, e);
-                std::string key;
+                std::string_view key;
                 if (p < e && (*p == '"' || *p == '\'')) {
                     if (!parse_quoted(p, e, key, line)) return false;
                 } else {
@@ -105,14 +132,15 @@ struct Parser {
                     while (p < e && *p != ':' && *p != ',' && *p != '}') ++p;
                     const char* ke = p;
                     while (ke > b && ke[-1] == ' ') --ke;
-                    key.assign(b, ke);
+                    key = std::string_view(b, (size_t)(ke - b));
                 }
                 skip_ws(p, e);
                 if (p >= e || *p != ':') return fail(line, "expected ':' in flow mapping");
                 ++p;
                 Node val;
                 if (!parse_flow_value(p, e, val, line, true, depth + 1)) return false;
-                n.map.emplace_back(std::move(key), std::move(val));
+                val.key = key;
+                n.children.push_back(std::move(val));
                 skip_ws(p, e);
                 if (p < e && *p == ',') { ++p; continue; }
                 if (p < e && *p == '}') { ++p; return true; }
@@ -144,7 +172,7 @@ struct Parser {
     // ---- block structure -----------------------------------------------------------------------------
     static bool is_seq_item(const Line& l) { return l.n >= 1 && l.s[0] == '-' && (l.n == 1 || l.s[1] == ' '); }
     // Finds the "key:" split of a block-mapping line. Returns false if the line is not a mapping entry.
-    static bool split_key(const Line& l, std::string& key, const char*& rest_b, const char*& rest_e) {
+    static bool split_key(const Line& l, std::string_view& key, const char*& rest_b, const char*& rest_e) {
         const char* p = l.s;
         const char* e = l.s + l.n;
         if (p < e && (*p == '"' || *p == '\'')) {
@@ -152,7 +180,7 @@ struct Parser {
             const char* b = ++p;
             while (p < e && *p != q) ++p;
             if (p >= e) return false;
-            key.assign(b, p);
+            key = std::string_view(b, (size_t)(p - b));
             ++p;
             if (p >= e || *p != ':') return false;
         } else {
@@ -163,7 +191,7 @@ struct Parser {
                 ++p;
             }
             if (p >= e) return false;
-            key.assign(b, p);
+            key = std::string_view(b, (size_t)(p - b));
         }
         ++p;  // ':'
         while (p < e && *p == ' ') ++p;
@@ -180,7 +208,7 @@ struct Parser {
         const Line& l = lines[pos];
         out.line = l.no;
         if (is_seq_item(l)) return parse_seq(l.indent, out);
-        std::string key;
+        std::string_view key;
         const char *rb, *re;
         if (split_key(l, key, rb, re)) return parse_map(l.indent, out);
         // single-line scalar / flow collection
@@ -190,11 +218,13 @@ struct Parser {
     }
     bool parse_seq(int indent, Node& out) {
         out.kind = Node::SEQ;
+        out.children.reserve(8);
         while (pos < lines.size() && lines[pos].indent == indent && is_seq_item(lines[pos])) {
             Line& l = lines[pos];
             size_t off = 1;
             while (off < l.n && l.s[off] == ' ') ++off;
-            Node item;
+            out.children.emplace_back();          // built in place: nothing below touches out.children
+            Node& item = out.children.back();
             item.line = l.no;
             if (off >= l.n) {
                 ++pos;
@@ -205,21 +235,23 @@ struct Parser {
                 l.n -= off;
                 if (!parse_node(indent + 1, item)) return false;
             }
-            out.seq.push_back(std::move(item));
         }
         if (pos < lines.size() && lines[pos].indent > indent) return fail(lines[pos].no, "bad indentation in sequence");
         return true;
     }
     bool parse_map(int indent, Node& out) {
         out.kind = Node::MAP;
+        out.children.reserve(4);
         while (pos < lines.size() && lines[pos].indent == indent) {
             const Line& l = lines[pos];
             if (is_seq_item(l)) break;
-            std::string key;
+            std::string_view key;
             const char *rb, *re;
             if (!split_key(l, key, rb, re)) return fail(l.no, "expected 'key: value'");
-            Node val;
+            out.children.emplace_back();
+            Node& val = out.children.back();
             val.line = l.no;
+            val.key = key;
             if (rb < re) {
                 if (!parse_inline(rb, re, val, l.no)) return false;
                 ++pos;
@@ -233,7 +265,6 @@ struct Parser {
                     val.kind = Node::NUL;
                 }
             }
-            out.map.emplace_back(std::move(key), std::move(val));
         }
         if (pos < lines.size() && lines[pos].indent > indent) return fail(lines[pos].no, "bad indentation in mapping");
         return true;
@@ -265,6 +296,7 @@ bool parse(const char* text, size_t len, Node& root, std::string& err) {
         const char* c = b;
         char q = 0;
         const char* ce = le;
+        if (!memchr(b, '#', (size_t)(le - b))) c = le;   // no '#' on the line (nearly every line): nothing to strip
         for (; c < le; ++c) {
             if (q) {
                 if (*c == q) q = 0;
@@ -293,6 +325,8 @@ bool parse(const char* text, size_t len, Node& root, std::string& err) {
         err = "line " + std::to_string(ps.lines[ps.pos].no) + ": unexpected content (indentation?)";
         return false;
     }
+    root.pool.reset(ps.pool);
+    ps.pool = nullptr;
     return true;
 }
 

@@ -244,6 +244,17 @@ def selftest_shared_division(n_pairs: int, seed: int = 1, device: int = 0):
     return int(v[0]), int(v[1])
 
 
+def texture_store_stats() -> dict:
+    """fw_texture_store_stats: commits served from a resident array, uploads, arrays resident now and their bytes."""
+    v = np.zeros(4, np.uint64)
+    N.check(N.lib().fw_texture_store_stats(N.ptr(v)))
+    return {"hits": int(v[0]), "uploads": int(v[1]), "arrays": int(v[2]), "bytes": int(v[3])}
+
+
+def release_cached_memory():
+    N.check(N.lib().fw_release_cached_memory())
+
+
 def resolve_host(sums: np.ndarray, samples: int, gamma: float, device: int = 0) -> np.ndarray:
     """render.rs:184-189 for a host fp32 sum buffer (H, W, 3) -> u8 image, on the GPU (fw_resolve_host)."""
     s = np.ascontiguousarray(sums, np.float32)

@@ -199,6 +199,11 @@ int fw_set_profiling(fw_scene* scene, int enabled);
 /* Render-time device buffers (path-state streams, ~1.2 GB at the default batch size) are cached per device
  * across scenes; this frees every cached context that is not in use. */
 int fw_release_cached_memory(void);
+/* Texture store (no reference counterpart): texels handed to fw_scene_set_image / fw_scene_set_hdr are hashed, and a scene
+ * whose texels are already resident on its device shares that array instead of copying and uploading them again
+ * (FW_TEXTURE_CACHE=0 in the environment disables the lookup).  out = {commits served from a resident array, uploads,
+ * arrays resident now, their bytes}. */
+int fw_texture_store_stats(uint64_t out[4]);
 /* Maximum number of paths in flight per batch (0 = default). */
 int fw_set_batch_paths(fw_scene* scene, uint64_t paths);
 

@@ -223,3 +223,65 @@ def test_black_environment_miss_shortcut_is_exact(monkeypatch):
     assert np.array_equal(np.isnan(full), np.isnan(fast))
     ok = ~np.isnan(full)
     assert np.array_equal(full[ok], fast[ok])
+
+
+def _store_stats():
+    from firework_b200.engine import texture_store_stats
+    return texture_store_stats()
+
+
+def test_texture_store_shares_resident_texels_and_sees_changed_content(monkeypatch):
+    """Texture store (api.cu): a second scene handed the same HDR map / image shares the resident array (no upload, identical
+    image, also while the first scene is still alive); changed texels of the same geometry are uploaded again and the image
+    follows them; FW_TEXTURE_CACHE=0 uploads every time and gives the same images."""
+    from conftest import params_for, scene_text
+    from firework_b200.assets import synthetic_hdr
+    from firework_b200.engine import release_cached_memory
+    release_cached_memory()
+    hdr_a = synthetic_hdr(512, 256, 3)
+    hdr_b = hdr_a.copy()
+    hdr_b[:, :256] *= 0.25
+    text = scene_text("hdri_test")
+    key = [l for l in text.splitlines() if "synthetic_hdr" in l][0].split("value:")[1].strip()
+    p = params_for("hdri_test", 200, 100, 8, seed=4)
+
+    def render(hdr, keep=False):
+        before = _store_stats()
+        ns = NativeScene(text, assets={key: hdr})
+        rgb, s, _ = ns.render(p)
+        after = _store_stats()
+        bytes_up = ns.device_bytes()
+        if not keep:
+            ns.close()
+        return rgb, s, after["hits"] - before["hits"], after["uploads"] - before["uploads"], bytes_up, ns
+
+    rgb1, s1, hit1, up1, bytes1, _ = render(hdr_a)
+    assert (hit1, up1) == (0, 1) and bytes1 >= hdr_a.shape[0] * hdr_a.shape[1] * 16
+    rgb2, s2, hit2, up2, bytes2, live = render(hdr_a, keep=True)          # same content: shared, nothing uploaded
+    assert (hit2, up2) == (1, 0) and bytes2 < 512 * 256 * 16
+    assert np.array_equal(s1, s2) and np.array_equal(rgb1, rgb2)
+    rgb3, s3, hit3, up3, _, _ = render(hdr_a)                               # ... also while another scene is using the array
+    assert (hit3, up3) == (1, 0) and np.array_equal(s1, s3)
+    live.close()
+    rgb4, s4, hit4, up4, _, _ = render(hdr_b)                               # same geometry, other content: uploaded
+    assert (hit4, up4) == (0, 1) and not np.array_equal(s1, s4)
+    rgb5, s5, hit5, up5, _, _ = render(hdr_a)                               # the first content again (idle array refilled or kept)
+    assert np.array_equal(s1, s5)
+    monkeypatch.setenv("FW_TEXTURE_CACHE", "0")
+    rgb6, s6, hit6, up6, _, _ = render(hdr_b)
+    assert (hit6, up6) == (0, 1) and np.array_equal(s4, s6)
+    monkeypatch.delenv("FW_TEXTURE_CACHE")
+    # image textures (RGBA8) go through the same store
+    pe = params_for("earth", 160, 160, 4, seed=2)
+    from conftest import native_scene
+    outs = []
+    for _ in range(2):
+        before = _store_stats()
+        ns = native_scene("earth")
+        _, s, _ = ns.render(pe, want_rgb=False)
+        ns.close()
+        after = _store_stats()
+        outs.append((s, after["hits"] - before["hits"], after["uploads"] - before["uploads"]))
+    assert outs[1][1] >= 1 and outs[1][2] == 0 and np.array_equal(outs[0][0], outs[1][0])
+    release_cached_memory()
+    assert _store_stats()["arrays"] == 0

@@ -55,6 +55,31 @@ def test_render_multi_matches_single_gpu(name, w, h, spp, mode):
     ns.close()
 
 
+def test_texture_store_hit_on_another_device_reads_the_texels_back():
+    """fw_scene_set_hdr skips the host copy when the content is resident anywhere; a commit onto a device that does not
+    hold it must fetch the texels from the array that does (api.cu host_texels)."""
+    if _n_devices() < 2:
+        pytest.skip("needs two CUDA devices")
+    from conftest import scene_text, ASSETS
+    from firework_b200.engine import NativeScene, release_cached_memory, texture_store_stats
+    release_cached_memory()
+    text = scene_text("hdri_test")
+    p = params_for("hdri_test", 200, 100, 8, seed=5)
+    a = NativeScene(text, device=0, asset_dir=ASSETS)
+    _, sa, _ = a.render(p, want_rgb=False)
+    before = texture_store_stats()
+    b = NativeScene(text, device=1, asset_dir=ASSETS)        # set-time hit (device 0), commit on device 1
+    _, sb, _ = b.render(p, want_rgb=False)
+    after = texture_store_stats()
+    assert after["uploads"] - before["uploads"] == 1 and after["arrays"] == 2
+    assert np.array_equal(sa, sb)
+    _, sm, _ = b.render_multi(p, 2, devices=[1, 0], want_rgb=False)   # its replica on device 0 shares a's array
+    assert texture_store_stats()["arrays"] == 2
+    assert np.allclose(sm, sa, rtol=2e-5, atol=1e-5)
+    a.close(); b.close()
+    release_cached_memory()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
