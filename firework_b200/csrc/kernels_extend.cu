@@ -100,6 +100,9 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_EXTEND_MIN_BLOCKS) extend_pass1_s
             const size_t slot_in = (size_t)seg_base + e0 + threadIdx.x;
             float4 ro = ld_stream(&ps.xo[bounce & 1][slot_in]), rd = ld_stream(&ps.xd[bounce & 1][slot_in]);
             o = f3(ro); d = f3(rd); path = __float_as_uint(ro.w);
+            if (FW_EXTEND_PREFETCH && e0 + FW_BLOCK + threadIdx.x < in_count) {
+                prefetch_l2(&ps.xo[bounce & 1][slot_in + FW_BLOCK]); prefetch_l2(&ps.xd[bounce & 1][slot_in + FW_BLOCK]);
+            }
             if (nan_direction(d)) {
                 nan_direction_winner(S.nan_bvh_obj, S.nan_bvh_prim, w);
             } else {

@@ -30,7 +30,7 @@ FW_DEV float4 ld_stream(const float4* p) { return FW_STREAM_HINTS ? __ldcs(p) : 
 #define FW_PREFETCH 1
 #endif
 // The record a shade thread will need in its NEXT iteration is FW_BLOCK slots ahead: ask L2 for it now (no register
-// cost).  Measured: +1-2 % on the latency-bound shade kernels, nothing on the issue-bound extend kernels (not used there).
+// cost).  Measured: +1-2 % on the latency-bound shade kernels, +0.3 ... +0.6 % on the extend kernels (FW_EXTEND_PREFETCH).
 FW_DEV void prefetch_l2(const void* p) {
     if (FW_PREFETCH) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -198,6 +198,9 @@ FW_DEV HitIn get_hit(const PathState& ps, uint32_t slot) {
 
 // Common shape of the extend kernels: one block per segment, FW_BLOCK rays per iteration.  The body sets `w`
 // for valid lanes; the epilogue sorts the ray into its shade queue.
+#ifndef FW_EXTEND_PREFETCH
+#define FW_EXTEND_PREFETCH 1   // L2 prefetch of the next iteration's ray records: +0.3 ... +0.6 % (profiles/r02_variants.md)
+#endif
 #define FW_EXTEND_PROLOGUE(NQ_OUT)                                                                         \
     __shared__ uint32_t s_fill[FW_NUM_QUEUES];                                                               \
     const uint32_t in_count = counter_row(ps, bounce, FW_Q_EXTEND)[blockIdx.x];                              \
@@ -210,6 +213,9 @@ FW_DEV HitIn get_hit(const PathState& ps, uint32_t slot) {
             const size_t slot_in = (size_t)blockIdx.x * ps.seg_cap + e0 + threadIdx.x;                       \
             float4 ro = ld_stream(&ps.xo[bounce & 1][slot_in]), rd = ld_stream(&ps.xd[bounce & 1][slot_in]);     \
             o = f3(ro); d = f3(rd); path = __float_as_uint(ro.w);                                            \
+            if (FW_EXTEND_PREFETCH && e0 + FW_BLOCK + threadIdx.x < in_count) {                              \
+                prefetch_l2(&ps.xo[bounce & 1][slot_in + FW_BLOCK]); prefetch_l2(&ps.xd[bounce & 1][slot_in + FW_BLOCK]); \
+            }                                                                                                \
         }                                                                                                    \
         Winner w;                                                                                            \
         w.found = false; w.t = 0.0f; w.obj = -1; w.rank = -1; w.h.t = 0.0f; w.h.prim = 0;                    \
