@@ -43,7 +43,7 @@ EXPORTS = [
     "fw_render_accumulate_device", "fw_resolve_device", "fw_primary_rays", "fw_first_hit", "fw_scatter_step",
     "fw_env_sample", "fw_texture_sample", "fw_material_texture", "fw_camera", "fw_last_error", "fw_version",
     "fw_device_count", "fw_measure_peaks", "fw_selftest_shared_division", "fw_obj_load", "fw_obj_num_models",
-    "fw_obj_model_name", "fw_obj_model_sizes", "fw_obj_model_copy", "fw_obj_destroy", "fw_hdr_load", "fw_hdr_free", "fw_set_profiling", "fw_set_batch_paths", "fw_release_cached_memory", "fw_texture_store_stats",
+    "fw_obj_model_name", "fw_obj_model_sizes", "fw_obj_model_copy", "fw_obj_destroy", "fw_hdr_load", "fw_hdr_free", "fw_image_load", "fw_image_free", "fw_png_write", "fw_set_profiling", "fw_set_batch_paths", "fw_release_cached_memory", "fw_texture_store_stats",
     "fw_resolve_host", "fw_render_multi", "fw_scene_walk_info", "fw_first_hit_wavefront",
 ]
 
@@ -88,6 +88,11 @@ def lib():
         L.fw_hdr_load.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.POINTER(C.c_float))]
         L.fw_hdr_free.argtypes = [C.POINTER(C.c_float)]
         L.fw_hdr_free.restype = None
+        L.fw_image_load.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.POINTER(C.c_uint8))]
+        L.fw_image_free.argtypes = [C.POINTER(C.c_uint8)]
+        L.fw_image_free.restype = None
+        L.fw_png_write.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.fw_texture_store_stats.argtypes = [C.c_void_p]
         L.fw_scene_destroy.restype = None
         for name in ("fw_scene_num_assets", "fw_scene_num_objects", "fw_scene_num_nodes"):
             getattr(L, name).argtypes = [C.c_void_p]

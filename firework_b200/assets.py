@@ -100,3 +100,25 @@ def load_obj(path: str):
         return models
     finally:
         L.fw_obj_destroy(h)
+
+
+def load_image_native(path: str) -> np.ndarray:
+    """PNG / baseline JPEG -> (H, W, 4) u8 RGBA through the library's own decoder (fw_image_load, csrc/images.cpp) — what the
+    native command-line driver uses; `load_asset` decodes with PIL so that the oracle and the GPU see one texel array."""
+    import ctypes as C
+    from . import _native as N
+    L = N.lib()
+    w, h = C.c_uint32(), C.c_uint32()
+    p = C.POINTER(C.c_uint8)()
+    N.check(L.fw_image_load(path.encode(), C.byref(w), C.byref(h), C.byref(p)))
+    try:
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value, 4)).copy()
+    finally:
+        L.fw_image_free(p)
+
+
+def write_png(path: str, rgb: np.ndarray) -> None:
+    """(H, W, 3) u8 -> PNG through fw_png_write (window.rs `save_image`)."""
+    from . import _native as N
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    N.check(N.lib().fw_png_write(path.encode(), rgb.shape[1], rgb.shape[0], N.ptr(rgb)))

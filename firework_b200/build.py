@@ -16,8 +16,10 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libfirework_b200.so")
 STATIC_LIB = os.path.join(HERE, "libfirework_b200.a")
+CLI = os.path.join(HERE, "bin", "firework")          # native driver (csrc/cli_main.cpp), links the static archive
+LINK_LIBS = ["-lcudart_static", "-lz", "-ldl", "-lpthread", "-lrt"]   # zlib: PNG inflate / deflate (images.cpp), .yml.gz (cli)
 SOURCES = ["api.cu", "multi_gpu.cu", "kernels_extend.cu", "kernels_walk.cu", "kernels_shade.cu", "kernels_probe.cu",
-           "scene_host.cpp", "yaml_lite.cpp", "formats.cpp"]
+           "scene_host.cpp", "yaml_lite.cpp", "formats.cpp", "images.cpp"]
 HEADERS = ["fw_types.h", "scene_host.h", "yaml_lite.h", "device_math.cuh", "intersect.cuh", "shade.cuh", "wavefront.cuh",
            "wavefront_types.h", "launch.h", "api_internal.h", "walk.cuh", os.path.join("..", "..", "include", "firework_b200.h")]
 
@@ -34,7 +36,7 @@ def _sources():
 
 
 def _deps():
-    return [os.path.join(CSRC, s) for s in _sources() + HEADERS if os.path.exists(os.path.join(CSRC, s))] + [os.path.abspath(__file__)]
+    return [os.path.join(CSRC, s) for s in _sources() + HEADERS + ["cli_main.cpp"] if os.path.exists(os.path.join(CSRC, s))] + [os.path.abspath(__file__)]
 
 
 def needs_build(target: str = LIB) -> bool:
@@ -58,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     extra = os.environ.get("FW_NVCC_EXTRA", "").split()
     variant = bool(extra) or out != LIB          # experiment builds get their own object directory
     obj_dir = OBJ_DIR + ("_" + os.path.splitext(os.path.basename(out))[0] if variant else "")
-    if not force and not variant and not needs_build(LIB) and not needs_build(STATIC_LIB):
+    if not force and not variant and not needs_build(LIB) and not needs_build(STATIC_LIB) and not needs_build(CLI):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(obj_dir, exist_ok=True)
@@ -83,7 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # -ldl: NCCL is bound at run time (multi_gpu.cu dlopens libnccl.so.2 when fw_render_multi is first called)
     # (linked with g++ directly: `nvcc -shared` would add a device-link stub compiled for its default sm_52)
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
-    r = subprocess.run(["/usr/bin/g++", "-shared", "-o", out] + objs + ["-L" + cuda_lib, "-lcudart_static", "-ldl", "-lpthread", "-lrt"],
+    r = subprocess.run(["/usr/bin/g++", "-shared", "-o", out] + objs + ["-L" + cuda_lib] + LINK_LIBS,
                        capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -95,6 +97,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("archiving libfirework_b200.a failed")
+        # the native command-line driver: plain g++ against the static archive, exactly what a build.rs / Makefile would do
+        os.makedirs(os.path.dirname(CLI), exist_ok=True)
+        r = subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-o", CLI, os.path.join(CSRC, "cli_main.cpp"), STATIC_LIB, "-L" + cuda_lib] + LINK_LIBS,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("building the firework command-line driver failed")
     if verbose:
         print("\n".join(logs))
     return out

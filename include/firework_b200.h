@@ -174,7 +174,8 @@ int fw_device_count(void);
  *                examples/teapot.rs:17-64): one model per `o` / `g` group, fan triangulation, one vertex per distinct
  *                v/vt/vn triple in order of first use.  The arrays feed TriangleMesh::new (src/objects/mesh.rs:36-72).
  * fw_hdr_load  : Radiance RGBE .hdr -> fp32 RGB, row 0 = top, as image 0.23.9 `HdrDecoder::read_image_hdr`
- *                (examples/hdri_test.rs:45-67); the result feeds fw_scene_set_hdr.  Free with fw_hdr_free. */
+ *                (examples/hdri_test.rs:45-67); the result feeds fw_scene_set_hdr.  Free with fw_hdr_free.
+ * The native command-line driver built on these (csrc/cli_main.cpp -> firework_b200/bin/firework) is src/main.rs. */
 typedef struct fw_obj fw_obj;
 int fw_obj_load(const char* path, fw_obj** out);
 int fw_obj_num_models(const fw_obj* obj);
@@ -184,6 +185,13 @@ int fw_obj_model_copy(const fw_obj* obj, int model, float* positions, float* nor
 void fw_obj_destroy(fw_obj* obj);
 int fw_hdr_load(const char* path, uint32_t* width, uint32_t* height, float** rgb);
 void fw_hdr_free(float* rgb);
+/* fw_image_load: PNG (non-interlaced) or baseline JPEG -> RGBA8, row 0 = top, as `image::open(path)...to_rgba()` in
+ *                ImageTexture::from_path / sample (src/texture.rs:285-292, 304); feeds fw_scene_set_image.  Free with
+ *                fw_image_free.
+ * fw_png_write : width*height*3 u8 (what fw_render returns) -> PNG file, as window.rs `save_image` (src/main.rs:55). */
+int fw_image_load(const char* path, uint32_t* width, uint32_t* height, uint8_t** rgba);
+void fw_image_free(uint8_t* rgba);
+int fw_png_write(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb);
 
 /* Self-test of the shared-reciprocal division used by the linear-scan kernels (t = (k - o[a]) / d[a],
  * src/objects/rect.rs:49) against the hardware's IEEE division on n_pairs pseudo-random / adversarial operand pairs.

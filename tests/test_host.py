@@ -230,15 +230,15 @@ def test_radiance_hdr_decoder(tmp_path, rle):
 def test_asset_loaders_report_errors(tmp_path):
     from firework_b200._native import FireworkError
     from firework_b200.assets import load_hdr, load_obj
-    with pytest.raises(FireworkError):
+    with pytest.raises(N.FireworkError):
         load_obj(str(tmp_path / "missing.obj"))
     bad = tmp_path / "bad.obj"
     bad.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n")
-    with pytest.raises(FireworkError, match="bad vertex index"):
+    with pytest.raises(N.FireworkError, match="bad vertex index"):
         load_obj(str(bad))
     nothdr = tmp_path / "x.hdr"
     nothdr.write_bytes(b"P6\n1 1\n255\n\0\0\0")
-    with pytest.raises(FireworkError, match="not a Radiance"):
+    with pytest.raises(N.FireworkError, match="not a Radiance"):
         load_hdr(str(nothdr))
 
 
@@ -312,11 +312,11 @@ def test_hostile_inputs_are_rejected_not_crashed(tmp_path):
     from firework_b200._native import FireworkError, FwParams, FwStats
     from firework_b200.assets import load_hdr
     from firework_b200.engine import NativeScene
-    with pytest.raises(FireworkError, match="nested too deeply"):
+    with pytest.raises(N.FireworkError, match="nested too deeply"):
         NativeScene("render_objects: " + "[" * 100000 + "]" * 100000 + "\nmaterials: []\n", commit=False)
     big = tmp_path / "big.hdr"
     big.write_bytes(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2147483648 +X 2147483648\n" + b"\0" * 64)
-    with pytest.raises(FireworkError, match="unreasonable image size"):
+    with pytest.raises(N.FireworkError, match="unreasonable image size"):
         load_hdr(str(big))
     from conftest import params_for
     ns = native_scene("cornell_box", commit=False)
@@ -352,3 +352,113 @@ def test_checkpoint_fingerprint_guards_resume(tmp_path):
     assert render_fingerprint(a, ra) != render_fingerprint(b, ra)
     assert render_fingerprint(a, ra) != render_fingerprint(a, CONFIGS["cornell_box"].renderer(width=16, height=16, samples=4, seed=2))
     assert render_fingerprint(a, ra) != render_fingerprint(a, CONFIGS["cornell_box"].renderer(width=17, height=16, samples=4, seed=1))
+
+
+# ---- image files: PNG / JPEG in (ImageTexture::from_path, texture.rs:285-292), PNG out (window.rs save_image) -------------------
+def test_native_png_decoder_matches_pil_on_every_colour_type(tmp_path):
+    from PIL import Image
+    from firework_b200.assets import load_image_native
+    from firework_b200.scenes import SCENE_DIR
+    p = os.path.join(SCENE_DIR, "assets", "uvmap.png")
+    assert np.array_equal(load_image_native(p), np.asarray(Image.open(p).convert("RGBA")))
+    rng = np.random.default_rng(3)
+    smooth = (np.add.outer(np.arange(37), np.arange(53)) * 3 % 256).astype(np.uint8)      # exercises the Sub / Up / Avg / Paeth filters
+    cases = {
+        "rgb": Image.fromarray(np.stack([smooth, smooth.T[:37, :53] if False else smooth[::-1], rng.integers(0, 256, smooth.shape, dtype=np.uint8)], -1), "RGB"),
+        "rgba": Image.fromarray(rng.integers(0, 256, (19, 23, 4), dtype=np.uint8), "RGBA"),
+        "gray": Image.fromarray(smooth, "L"),
+        "gray_alpha": Image.fromarray(rng.integers(0, 256, (11, 7, 2), dtype=np.uint8), "LA"),
+        "palette": Image.fromarray(rng.integers(0, 256, (31, 17, 3), dtype=np.uint8), "RGB").quantize(16),
+        "bilevel": Image.fromarray((rng.random((13, 29)) > 0.5)),
+    }
+    for name, im in cases.items():
+        f = str(tmp_path / f"{name}.png")
+        im.save(f, optimize=(name != "rgb"))
+        got = load_image_native(f)
+        want = np.asarray(Image.open(f).convert("RGBA"))
+        assert got.shape == want.shape, name
+        assert np.array_equal(got, want), name
+
+
+def test_native_jpeg_decoder_is_within_rounding_of_libjpeg():
+    """A JPEG decoder is defined up to its IDCT rounding and chroma upsampling; this one (accurate IDCT, triangle upsampling,
+    libjpeg's fixed-point colour conversion) agrees with PIL's libjpeg on 98 % of the values of earthmap.jpg, max |diff| 3."""
+    from PIL import Image
+    from firework_b200.assets import load_image_native
+    from firework_b200.scenes import SCENE_DIR
+    p = os.path.join(SCENE_DIR, "assets", "earthmap.jpg")
+    got = load_image_native(p).astype(int)
+    want = np.asarray(Image.open(p).convert("RGBA")).astype(int)
+    assert got.shape == want.shape
+    d = np.abs(got - want)
+    assert d.max() <= 4 and (d > 0).mean() < 0.03 and d.mean() < 0.03
+
+
+def test_native_jpeg_decoder_sampling_modes_and_restarts(tmp_path):
+    from PIL import Image
+    from firework_b200.assets import load_image_native
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:61, 0:83]
+    img = np.stack([(xx * 3) % 256, (yy * 4) % 256, ((xx + yy) * 2) % 256], -1).astype(np.uint8)
+    img = (img * 0.8 + rng.integers(0, 50, img.shape)).astype(np.uint8)
+    for sub, name in ((0, "444"), (1, "422"), (2, "420")):
+        f = str(tmp_path / f"s{name}.jpg")
+        Image.fromarray(img, "RGB").save(f, quality=90, subsampling=sub)
+        got = load_image_native(f).astype(int)
+        want = np.asarray(Image.open(f).convert("RGBA")).astype(int)
+        d = np.abs(got - want)
+        assert got.shape == want.shape and d.max() <= 4 and d.mean() < 0.2, (name, d.max(), d.mean())
+    f = str(tmp_path / "restart.jpg")
+    try:
+        Image.fromarray(img, "RGB").save(f, quality=90, subsampling=2, restart_marker_blocks=3)
+        has_restart = b"\xff\xdd" in open(f, "rb").read()
+    except TypeError:
+        has_restart = False
+    if has_restart:   # DRI + RSTn markers (Pillow >= 10.2 writes them on request)
+        d = np.abs(load_image_native(f).astype(int) - np.asarray(Image.open(f).convert("RGBA")).astype(int))
+        assert d.max() <= 4 and d.mean() < 0.2
+    f = str(tmp_path / "gray.jpg")
+    Image.fromarray(img[..., 0], "L").save(f, quality=85)
+    d = np.abs(load_image_native(f).astype(int) - np.asarray(Image.open(f).convert("RGBA")).astype(int))
+    assert d.max() <= 2
+    f = str(tmp_path / "prog.jpg")
+    Image.fromarray(img, "RGB").save(f, progressive=True)
+    with pytest.raises(N.FireworkError, match="progressive"):
+        load_image_native(f)
+
+
+def test_png_writer_round_trips(tmp_path):
+    from PIL import Image
+    from firework_b200.assets import load_image_native, write_png
+    rng = np.random.default_rng(9)
+    rgb = rng.integers(0, 256, (45, 67, 3), dtype=np.uint8)
+    f = str(tmp_path / "out.png")
+    write_png(f, rgb)
+    assert np.array_equal(np.asarray(Image.open(f).convert("RGB")), rgb)
+    assert np.array_equal(load_image_native(f)[..., :3], rgb)
+    with pytest.raises(N.FireworkError):
+        load_image_native(str(tmp_path / "missing.png"))
+    open(tmp_path / "junk.png", "wb").write(b"\x89PNG\r\n\x1a\n" + b"\0" * 40)
+    with pytest.raises(N.FireworkError):
+        load_image_native(str(tmp_path / "junk.png"))
+
+
+def test_native_cli_mirrors_main_rs_arguments(tmp_path):
+    """csrc/cli_main.cpp -> firework_b200/bin/firework: src/main.rs:6-20 options; errors are messages + exit code 1, and without
+    a CUDA device the render refuses to start (no CPU fallback)."""
+    import subprocess
+    from firework_b200.build import CLI
+    assert os.path.exists(CLI)
+    r = subprocess.run([CLI, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--scene-file" in r.stdout and "--samples" in r.stdout
+    r = subprocess.run([CLI, "-s", "4"], capture_output=True, text=True)
+    assert r.returncode == 1 and "--scene-file" in r.stderr
+    r = subprocess.run([CLI, "--scene-file", str(tmp_path / "nope.yml"), "-s", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open scene file" in r.stderr
+    bad = tmp_path / "bad.yml"
+    bad.write_text("render_objects: 7\n")
+    r = subprocess.run([CLI, "--scene-file", str(bad), "-s", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("error: scene")
+    if N.lib().fw_device_count() == 0:
+        r = subprocess.run([CLI, "--scene-file", CONFIGS["conics"].path(), "-s", "1", "-o", str(tmp_path / "x.png")], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr and not os.path.exists(tmp_path / "x.png")
