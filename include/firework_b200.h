@@ -4,11 +4,12 @@
  *
  *     Renderer::render(&self, scene: Scene) -> Vec<Color>            (reference src/render.rs:109)
  *
- * reached from src/main.rs:42 and every examples/*.rs.  `Scene` holds only trait objects
+ * reached from src/main.rs:42 and every file under examples/.  `Scene` holds only trait objects
  * (src/scene.rs:20-24), so the type-erased form any host can hand over is the serde document
  * `serde_yaml::to_string(&scene)` (src/scene.rs:18, src/serde_compat.rs) — that text is what
  * fw_scene_from_yaml takes.  INTEGRATION.md shows the Rust binding (`extern "C"` + build.rs) a
- * maintainer would add to call this from `Renderer::render`.
+ * maintainer would add to call this from `Renderer::render`; include/firework.hpp is a C++ mirror of the crate's public
+ * builder API on top of this header (examples/ restates three of the crate's examples with it).
  *
  * Conventions: plain pointers and sizes; the caller owns every buffer it passes; the library owns
  * fw_scene until fw_scene_destroy; every call returns 0 on success or a negative fw_status, and

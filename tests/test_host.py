@@ -462,3 +462,31 @@ def test_native_cli_mirrors_main_rs_arguments(tmp_path):
     if N.lib().fw_device_count() == 0:
         r = subprocess.run([CLI, "--scene-file", CONFIGS["conics"].path(), "-s", "1", "-o", str(tmp_path / "x.png")], capture_output=True, text=True)
         assert r.returncode == 1 and "no CUDA device" in r.stderr and not os.path.exists(tmp_path / "x.png")
+
+
+def _build_example(name, out_dir):
+    """g++ against the static archive: the link line of INTEGRATION.md."""
+    import subprocess
+    from firework_b200.build import STATIC_LIB
+    exe = os.path.join(str(out_dir), name)
+    cuda_lib = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-o", exe, os.path.join(REPO, "examples", name + ".cpp"), STATIC_LIB,
+                        "-L" + cuda_lib, "-lcudart_static", "-lz", "-ldl", "-lpthread", "-lrt"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_api_mirror_serialises_the_examples_like_the_python_mirror(tmp_path):
+    """include/firework.hpp (C++ mirror of the crate's builder API) and examples/*.cpp (the crate's examples restated with it):
+    `Scene::to_yaml` must be the document the Python mirror writes for the same example — byte for byte."""
+    import subprocess
+    from firework_b200 import scenes
+    for name, make in (("cornell_box", scenes.cornell_box), ("earth", scenes.earth_scene), ("volume_test", scenes.volume_scene)):
+        exe = _build_example(name, tmp_path)
+        r = subprocess.run([exe, "--yaml"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == make().to_yaml(), name
+        h = C.c_void_p()
+        data = r.stdout.encode()
+        assert N.lib().fw_scene_from_yaml(data, len(data), C.byref(h)) == 0      # and the native loader takes it
+        N.lib().fw_scene_destroy(h)
