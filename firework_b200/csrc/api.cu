@@ -791,14 +791,21 @@ int fw_camera(const fw_params* p, float out[24]) {
     out[22] = out[23] = 0.0f;
     return FW_OK;
 }
-int fw_release_cached_memory(void) {
+// Idle render contexts keep their path state (gigabytes each) for the next scene; when an allocation fails they are the first
+// thing to give back.  Returns how many were destroyed.
+static size_t destroy_idle_contexts() {
     std::lock_guard<std::mutex> lk(g_ctx_mutex);
     std::vector<RenderCtx*> keep;
+    size_t n = 0;
     for (RenderCtx* c : g_ctx_cache) {
         if (c->in_use) keep.push_back(c);
-        else destroy_ctx(c);
+        else { destroy_ctx(c); ++n; }
     }
     g_ctx_cache.swap(keep);
+    return n;
+}
+int fw_release_cached_memory(void) {
+    destroy_idle_contexts();
     {
         std::lock_guard<std::mutex> lk2(g_staging_mutex);
         for (HdrStaging* h : g_staging)
@@ -1118,16 +1125,35 @@ int fw::render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStream_t
         const size_t per_path = 64 + 16 * FW_MAX_DEPTH + 16 + 16 + 48 * queues + (sc->plan.walk ? 8 + 16 * (size_t)sc->flat.n_top_meshes : 0);
         size_t free_b = 0, total_b = 0;
         FW_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const double budget = 0.8 * ((double)free_b + (double)sc->ctx->ps_cap * per_path);
+        double budget = 0.8 * ((double)free_b + (double)sc->ctx->ps_cap * per_path);
+        if ((double)cap * per_path > budget) {   // idle contexts of earlier scenes hold path state nobody is using
+            int cur = 0;
+            cudaGetDevice(&cur);
+            const size_t n_freed = destroy_idle_contexts();
+            cudaSetDevice(cur);
+            if (n_freed) {
+                FW_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                budget = 0.8 * ((double)free_b + (double)sc->ctx->ps_cap * per_path);
+            }
+        }
         while (cap > ((size_t)1 << 22) && (double)cap * per_path > budget) cap >>= 1;
     }
-    for (;;) {   // ... and halve it if the allocation still fails
+    for (bool freed_idle = false;;) {   // ... and if the allocation still fails: idle contexts give their memory back, then halve
         rc = ensure_path_state(sc, cap);
-        if (rc == FW_OK || cap <= ((size_t)1 << 20) || cudaPeekAtLastError() != cudaErrorMemoryAllocation) break;
+        if (rc == FW_OK || cudaPeekAtLastError() != cudaErrorMemoryAllocation) break;
         cudaGetLastError();
         free_path_state(sc->ctx->ps);
         free_walk(sc->ctx);
         sc->ctx->ps_cap = 0;
+        if (!freed_idle) {
+            freed_idle = true;
+            int cur = 0;
+            cudaGetDevice(&cur);
+            const size_t n = destroy_idle_contexts();
+            cudaSetDevice(cur);
+            if (n > 0) continue;   // same size again
+        }
+        if (cap <= ((size_t)1 << 20)) break;
         cap >>= 1;
     }
     if (rc != FW_OK) return rc;

@@ -55,10 +55,10 @@ FW_DEV float3 fold_radiance(const PathState& ps, uint32_t path, uint32_t bounce,
 // textures evaluated at a non-finite hit point).  The shade kernels raise ps.poison for such a value; without it the
 // whole kernel is a no-op and returns at once (no attenuation chain is read at all).
 template <bool BLACK_ENV>
-__global__ void __launch_bounds__(FW_BLOCK) miss_kernel(DeviceScene S, PathState ps, uint32_t bounce) {
+FW_DEV void miss_segment(const DeviceScene& S, const PathState& ps, uint32_t bounce, uint32_t seg) {
     if (BLACK_ENV && *reinterpret_cast<volatile uint32_t*>(ps.poison) == 0u) return;
-    const uint32_t total = counter_row(ps, bounce, MAT_MISS)[blockIdx.x];
-    const float4* qd = ps.hq[MAT_MISS].d + (size_t)blockIdx.x * ps.seg_cap;
+    const uint32_t total = counter_row(ps, bounce, MAT_MISS)[seg];
+    const float4* qd = ps.hq[MAT_MISS].d + (size_t)seg * ps.seg_cap;
     for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
         float4 rec = ld_stream(&qd[i]);
         uint32_t path = __float_as_uint(rec.w);
@@ -67,11 +67,15 @@ __global__ void __launch_bounds__(FW_BLOCK) miss_kernel(DeviceScene S, PathState
         st_stream(&ps.radiance[path], make_float4(c.x, c.y, c.z, 0.0f));
     }
 }
+template <bool BLACK_ENV>
+__global__ void __launch_bounds__(FW_BLOCK) miss_kernel(DeviceScene S, PathState ps, uint32_t bounce) {
+    miss_segment<BLACK_ENV>(S, ps, bounce, blockIdx.x);
+}
 
 // render.rs:20,25-28 with material.rs:174-180 — emissive surfaces end the path with their texture value
-__global__ void __launch_bounds__(FW_BLOCK) shade_emissive_kernel(DeviceScene S, PathState ps, uint32_t bounce) {
-    const uint32_t total = counter_row(ps, bounce, MAT_EMISSIVE)[blockIdx.x];
-    const uint32_t base = blockIdx.x * ps.seg_cap;
+FW_DEV void emissive_segment(const DeviceScene& S, const PathState& ps, uint32_t bounce, uint32_t seg) {
+    const uint32_t total = counter_row(ps, bounce, MAT_EMISSIVE)[seg];
+    const uint32_t base = seg * ps.seg_cap;
     for (uint32_t i = threadIdx.x; i < total; i += FW_BLOCK) {
         HitIn h = get_hit<MAT_EMISSIVE>(ps, base + i);
         HitRecord rec;
@@ -82,21 +86,20 @@ __global__ void __launch_bounds__(FW_BLOCK) shade_emissive_kernel(DeviceScene S,
         st_stream(&ps.radiance[h.path], make_float4(c.x, c.y, c.z, 0.0f));
     }
 }
+__global__ void __launch_bounds__(FW_BLOCK) shade_emissive_kernel(DeviceScene S, PathState ps, uint32_t bounce) {
+    emissive_segment(S, ps, bounce, blockIdx.x);
+}
 
 // Scattering materials: the next ray goes into the next extend queue, this vertex's attenuation into the chain.
 // Not launched for bounce == FW_MAX_DEPTH (render.rs:21: no scatter at depth 10; emit is zero).
 // The material kernels of one bounce run back to back and append to the same regions of the next extend queue.
+// The entries of material MAT's queue of one segment; s_fill[0] is the segment's open fill count of the next extend queue.
 template <int MAT>
-__global__ void __launch_bounds__(FW_BLOCK, FW_SHADE_MIN_BLOCKS) shade_scatter_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce) {
-    __shared__ uint32_t s_fill[1];
-    const uint32_t seg = blockIdx.x;
-    const uint32_t total = counter_row(ps, bounce, MAT)[seg];
-    if (total == 0) return;  // block-uniform
-    uint32_t* row_out = counter_row(ps, bounce + 1, FW_Q_EXTEND);
+FW_DEV void scatter_segment(const DeviceScene& S, const PathState& ps, const Batch& b, uint2 seed, uint32_t bounce, uint32_t seg, uint32_t total,
+                            uint32_t* s_fill) {
     const uint32_t base = seg * ps.seg_cap;
     float4* __restrict__ xo = ps.xo[(bounce + 1) & 1];
     float4* __restrict__ xd = ps.xd[(bounce + 1) & 1];
-    seg_open<1>(s_fill, ps, row_out, seg);
     for (uint32_t e0 = 0; e0 < total; e0 += FW_BLOCK) {
         uint32_t i = e0 + threadIdx.x;
         int mine = -1;
@@ -144,6 +147,16 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_SHADE_MIN_BLOCKS) shade_scatter_k
             st_stream(&xd[slot], make_float4(out.dir.x, out.dir.y, out.dir.z, 0.0f));
         }
     }
+}
+template <int MAT>
+__global__ void __launch_bounds__(FW_BLOCK, FW_SHADE_MIN_BLOCKS) shade_scatter_kernel(DeviceScene S, PathState ps, Batch b, uint2 seed, uint32_t bounce) {
+    __shared__ uint32_t s_fill[1];
+    const uint32_t seg = blockIdx.x;
+    const uint32_t total = counter_row(ps, bounce, MAT)[seg];
+    if (total == 0) return;  // block-uniform
+    uint32_t* row_out = counter_row(ps, bounce + 1, FW_Q_EXTEND);
+    seg_open<1>(s_fill, ps, row_out, seg);
+    scatter_segment<MAT>(S, ps, b, seed, bounce, seg, total, s_fill);
     seg_close<1>(s_fill, ps, row_out, seg);
 }
 

@@ -285,3 +285,33 @@ def test_texture_store_shares_resident_texels_and_sees_changed_content(monkeypat
     assert outs[1][1] >= 1 and outs[1][2] == 0 and np.array_equal(outs[0][0], outs[1][0])
     release_cached_memory()
     assert _store_stats()["arrays"] == 0
+
+
+def test_idle_contexts_give_their_memory_back_when_an_allocation_fails():
+    """Render contexts are cached with their path state (gigabytes at full batch size).  A process that has rendered many large
+    scenes must still be able to start a small one next to a live scene: on an allocation failure the idle contexts are
+    destroyed and the allocation is retried (api.cu destroy_idle_contexts)."""
+    from conftest import native_scene, params_for
+    from firework_b200.engine import release_cached_memory
+    release_cached_memory()
+    # four idle contexts: three grown to a full 128 Mi-path batch (~53 GB each for cornell_box's two materials), the fourth to what
+    # was left — the device is nearly full of memory nobody is using
+    held = []
+    for _ in range(4):
+        ns = native_scene("cornell_box")
+        ns.render(params_for("cornell_box", 2048, 2048, 32, seed=1), want_rgb=False, want_sum=False)   # 128 Mi paths
+        held.append(ns)
+    for ns in held:
+        ns.close()
+    live = native_scene("cornell_box")                               # takes one of them over
+    live.render(params_for("cornell_box", 256, 256, 4, seed=1), want_rgb=False, want_sum=False)
+    # random_spheres has materials cornell_box lacks: the context it takes over must add their queues at its full capacity
+    # (19 GB) — that allocation fails, the idle contexts are released, the render goes through
+    small = native_scene("random_spheres")
+    rgb, s, _ = small.render(params_for("random_spheres", 96, 64, 4, seed=2))
+    assert np.isfinite(s).all() and rgb.std() > 1
+    ref = native_scene("random_spheres")
+    _, s2, _ = ref.render(params_for("random_spheres", 96, 64, 4, seed=2))
+    assert np.array_equal(s, s2)
+    small.close(); ref.close(); live.close()
+    release_cached_memory()
