@@ -40,7 +40,7 @@ bool read_file(const char* path, std::vector<uint8_t>& out, std::string& err) {
 }
 
 uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
-constexpr uint64_t kMaxTexels = 1ull << 28;   // 16384 x 16384: a hostile header must not be able to ask for terabytes
+constexpr uint64_t kMaxTexels = 1ull << 26;   // 8192 x 8192: a hostile header must not be able to ask for gigabytes
 
 // ---- PNG ---------------------------------------------------------------------------------------------------
 int paeth(int a, int b, int c) {

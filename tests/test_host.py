@@ -490,3 +490,31 @@ def test_cpp_api_mirror_serialises_the_examples_like_the_python_mirror(tmp_path)
         data = r.stdout.encode()
         assert N.lib().fw_scene_from_yaml(data, len(data), C.byref(h)) == 0      # and the native loader takes it
         N.lib().fw_scene_destroy(h)
+
+
+def test_native_image_decoders_survive_damaged_files(tmp_path):
+    """Truncated and bit-flipped PNG / JPEG files must come back as an error (or as some image), never as a crash or a hang:
+    the decoders sit on the path of untrusted scene assets."""
+    from firework_b200.assets import load_image_native
+    from firework_b200.scenes import SCENE_DIR
+    rng = np.random.default_rng(11)
+    for name in ("uvmap.png", "earthmap.jpg"):
+        data = open(os.path.join(SCENE_DIR, "assets", name), "rb").read()
+        f = str(tmp_path / ("damaged_" + name))
+        outcomes = {"error": 0, "image": 0}
+        cases = [data[:n] for n in (0, 1, 7, 8, 20, 33, 100, 1000, len(data) // 2, len(data) - 1)]
+        for _ in range(60):
+            b = bytearray(data)
+            for _k in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(0, min(len(b), 4096) if rng.random() < 0.7 else len(b)))   # headers and tables are up front
+                b[pos] = int(rng.integers(0, 256))
+            cases.append(bytes(b))
+        for c in cases:
+            open(f, "wb").write(c)
+            try:
+                img = load_image_native(f)
+                assert img.ndim == 3 and img.shape[2] == 4 and img.shape[0] * img.shape[1] <= 1 << 26
+                outcomes["image"] += 1
+            except N.FireworkError:
+                outcomes["error"] += 1
+        assert outcomes["error"] >= 10, (name, outcomes)      # every truncation is an error
