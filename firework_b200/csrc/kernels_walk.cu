@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(FW_BLOCK, FW_WALK_MIN_BLOCKS) walk_mesh_kernel
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, active);
         const bool want_refill = (input_left && 32 - __popc(act) >= FW_WALK_REFILL_IDLE) || act == 0u;
-        if (npairs >= 32 || (want_refill && npairs > 0)) {
+        if (npairs >= FW_WALK_TEST_AT || (want_refill && npairs > 0)) {
             // ---- TEST: one pair per lane, the leaf's 1-2 triangles against the owning entry's ray (bvh.rs:119-133 over
             // Triangle items, mesh.rs:140-219)
             const int n = npairs < 32 ? npairs : 32;

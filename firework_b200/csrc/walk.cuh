@@ -98,6 +98,9 @@ struct WalkAux {
 #ifndef FW_WALK_CULL
 #define FW_WALK_CULL 2
 #endif
+#ifndef FW_WALK_TEST_AT
+#define FW_WALK_TEST_AT 32   // pairs gathered by a warp before it runs a test phase (fewer: bounds shrink sooner, test lanes idle)
+#endif
 #ifndef FW_WALK_ORDER_BOX
 #define FW_WALK_ORDER_BOX 1   // deferred children ordered by box entry (0: by the kz-slab entry they are culled by); teapot +1.8 %, suzanne 0
 #endif
