@@ -1173,6 +1173,7 @@ int fw::render_into(fw_scene* sc, const fw_params* p, float* d_sum, cudaStream_t
             b.s0 = p->sample_begin + s; b.ns = std::min(chunk, p->sample_count - s);
             b.width = p->width; b.height = p->height;
             b.npix_magic = np <= 1 ? 0xffffffffu : (uint32_t)((((uint64_t)1 << 32) + np - 1) / np);
+            b.width_magic = p->width <= 1 ? 0xffffffffu : (uint32_t)((((uint64_t)1 << 32) + p->width - 1) / p->width);
             if ((rc = run_batch(sc, cam, b, seed, p->use_bvh != 0, d_sum, st, tot, ev_next)) != FW_OK) return rc;
         }
     }
@@ -1349,6 +1350,7 @@ int fw_first_hit_wavefront(fw_scene* sc, int use_bvh, uint64_t seed, uint32_t n,
     Batch b;   // ray i = path i = "pixel" i of a one-sample batch: RNG key (pixel i, sample, bounce)
     b.pix0 = 0; b.npix = n; b.s0 = sample; b.ns = 1; b.width = n; b.height = 1;
     b.npix_magic = n <= 1 ? 0xffffffffu : (uint32_t)((((uint64_t)1 << 32) + n - 1) / n);
+    b.width_magic = b.npix_magic;   // width == n
     const uint2 sd = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     launch_probe_fill(ps, n, dO.as<float>(), dD.as<float>(), bounce, st);
     if (use_bvh && sc->plan.walk && sc->plan.two_pass) {

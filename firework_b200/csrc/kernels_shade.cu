@@ -18,7 +18,9 @@ __global__ void __launch_bounds__(FW_BLOCK) raygen_kernel(CameraRec cam, Batch b
         uint32_t pixel, sample;
         batch_path(b, p, pixel, sample);
         float3 o, d;
-        primary_ray(cam, b.width, b.height, pixel, sample, seed, o, d);
+        uint32_t row, px;
+        div_magic(pixel, b.width, b.width_magic, row, px);
+        primary_ray_at(cam, b.width, b.height, px, row, pixel, sample, seed, o, d);
         st_stream(&ps.xo[0][base + e], make_float4(o.x, o.y, o.z, __uint_as_float(p)));
         st_stream(&ps.xd[0][base + e], make_float4(d.x, d.y, d.z, 0.0f));
         st_stream(&ps.radiance[p], make_float4(0.0f, 0.0f, 0.0f, 0.0f));

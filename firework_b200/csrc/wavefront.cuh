@@ -52,10 +52,24 @@ FW_DEV void batch_path(const Batch& b, uint32_t p, uint32_t& pixel, uint32_t& sa
 }
 
 // render.rs:173-180 + camera.rs:109-116 + util.rs:31-33
+// x / n and x % n for any 32-bit x, n >= 1, magic = ceil(2^32 / n) (0xffffffff for n == 1): umulhi gives the quotient or one
+// more (one less for n == 1); one correction step makes it exact — no emulated 32-bit division.
+FW_DEV void div_magic(uint32_t x, uint32_t n, uint32_t magic, uint32_t& q, uint32_t& r) {
+    q = __umulhi(x, magic);
+    int rr = (int)(x - q * n);
+    if (rr < 0) { q -= 1u; rr += (int)n; }
+    else if (rr >= (int)n) { q += 1u; rr -= (int)n; }
+    r = (uint32_t)rr;
+}
+FW_DEV void primary_ray_at(const CameraRec& cam, uint32_t width, uint32_t height, uint32_t px, uint32_t row, uint32_t pixel, uint32_t sample,
+                           uint2 seed, float3& o, float3& d);
 FW_DEV void primary_ray(const CameraRec& cam, uint32_t width, uint32_t height, uint32_t pixel, uint32_t sample,
                         uint2 seed, float3& o, float3& d) {
-    uint32_t px = pixel % width;
-    uint32_t py = height - pixel / width;  // Coord::from_index: y counts down from `height`
+    primary_ray_at(cam, width, height, pixel % width, pixel / width, pixel, sample, seed, o, d);
+}
+FW_DEV void primary_ray_at(const CameraRec& cam, uint32_t width, uint32_t height, uint32_t px, uint32_t row, uint32_t pixel, uint32_t sample,
+                           uint2 seed, float3& o, float3& d) {
+    uint32_t py = height - row;  // Coord::from_index: y counts down from `height`
     RngKey key{seed, pixel, sample, 0u};
     PhiloxStream rng(key, STREAM_CAMERA);
     float u = ((float)px + rng.next()) / (float)width;

@@ -41,6 +41,7 @@ struct Batch {
     uint32_t pix0, npix, s0, ns;
     uint32_t width, height;
     uint32_t npix_magic;   // ceil(2^32 / npix) (0xffffffff for npix == 1): p / npix without the emulated 32-bit division
+    uint32_t width_magic;  // the same for `width` (pixel -> column / row in raygen)
 };
 
 struct FirstHitOut {
