@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -97,7 +98,14 @@ inline std::string fmt_f32(float v) {   // serde_yaml prints an f32 as the short
     char buf[40];
     auto r = std::to_chars(buf, buf + sizeof buf, (double)v);
     std::string s(buf, r.ptr);
-    if (s.find_first_of(".en") == std::string::npos) s += ".0";
+    const size_t e = s.find('e');
+    if (e != std::string::npos) {   // exponent without padding, mantissa with a fraction: 9.34e-5, 1.0e+21
+        std::string m = s.substr(0, e);
+        const int ex = std::atoi(s.c_str() + e + 1);
+        if (m.find('.') == std::string::npos) m += ".0";
+        return m + "e" + (ex < 0 ? "-" : "+") + std::to_string(ex < 0 ? -ex : ex);
+    }
+    if (s.find('.') == std::string::npos) s += ".0";
     return s;
 }
 inline std::string fmt_str(const std::string& v) {

@@ -470,7 +470,7 @@ def _build_example(name, out_dir):
     from firework_b200.build import STATIC_LIB
     exe = os.path.join(str(out_dir), name)
     cuda_lib = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
-    r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-o", exe, os.path.join(REPO, "examples", name + ".cpp"), STATIC_LIB,
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-ffp-contract=off", "-o", exe, os.path.join(REPO, "examples", name + ".cpp"), STATIC_LIB,
                         "-L" + cuda_lib, "-lcudart_static", "-lz", "-ldl", "-lpthread", "-lrt"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe
@@ -481,7 +481,8 @@ def test_cpp_api_mirror_serialises_the_examples_like_the_python_mirror(tmp_path)
     `Scene::to_yaml` must be the document the Python mirror writes for the same example — byte for byte."""
     import subprocess
     from firework_b200 import scenes
-    for name, make in (("cornell_box", scenes.cornell_box), ("earth", scenes.earth_scene), ("volume_test", scenes.volume_scene)):
+    for name, make in (("cornell_box", scenes.cornell_box), ("earth", scenes.earth_scene), ("volume_test", scenes.volume_scene),
+                       ("random_spheres", lambda: scenes.random_scene(scenes.SceneRng(12345)))):
         exe = _build_example(name, tmp_path)
         r = subprocess.run([exe, "--yaml"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
