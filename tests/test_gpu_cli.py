@@ -75,3 +75,47 @@ def test_cpp_examples_render_what_the_python_mirror_renders(tmp_path):
     assert np.array_equal(np.asarray(Image.open(out).convert("RGB")), want)
     r = subprocess.run([exe, "-s", "1", "--asset-dir", str(tmp_path / "nowhere")], capture_output=True, text=True)
     assert r.returncode == 1 and "not found" in r.stderr      # errors are messages, not aborts
+
+
+def test_checkpoints_move_between_the_native_and_the_python_driver(tmp_path):
+    """--checkpoint x.fwck: one file format for both drivers (cli_main.cpp / progressive.py).  A render stopped after 4 of 10
+    samples by one driver and finished by the other is the 10-sample render (up to the fp32 order of adding the chunks)."""
+    from PIL import Image
+    from firework_b200.__main__ import main
+    from firework_b200.build import CLI
+    from firework_b200.progressive import fwck_load
+    scene = CONFIGS["conics"].path()
+    size = ["--width", "240", "--height", "135", "--seed", "7"]
+
+    def img(p):
+        return np.asarray(Image.open(p).convert("RGB")).astype(int)
+
+    whole = str(tmp_path / "whole.png")
+    assert subprocess.run([CLI, "--scene-file", scene, "-s", "10", "-o", whole] + size, capture_output=True, text=True).returncode == 0
+    # native alone, in chunks
+    ck = str(tmp_path / "a.fwck")
+    r = subprocess.run([CLI, "--scene-file", scene, "-s", "10", "--chunk", "4", "--checkpoint", ck, "-o", str(tmp_path / "a.png")] + size,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    sums, done, seed, _ = fwck_load(ck)
+    assert done == 10 and seed == 7 and sums.shape == (135, 240, 3)
+    assert np.abs(img(tmp_path / "a.png") - img(whole)).max() <= 1
+    # native starts, python finishes
+    ck = str(tmp_path / "b.fwck")
+    assert subprocess.run([CLI, "--scene-file", scene, "-s", "4", "--checkpoint", ck, "-o", str(tmp_path / "b4.png")] + size,
+                          capture_output=True, text=True).returncode == 0
+    assert fwck_load(ck)[1] == 4
+    assert main(["--scene-file", scene, "-s", "10", "--chunk", "3", "--checkpoint", ck, "-o", str(tmp_path / "b.png")] + size) == 0
+    assert fwck_load(ck)[1] == 10
+    assert np.abs(img(tmp_path / "b.png") - img(whole)).max() <= 1
+    # python starts, native finishes
+    ck = str(tmp_path / "c.fwck")
+    assert main(["--scene-file", scene, "-s", "4", "--checkpoint", ck, "-o", str(tmp_path / "c4.png")] + size) == 0
+    r = subprocess.run([CLI, "--scene-file", scene, "-s", "10", "--chunk", "5", "--checkpoint", ck, "-o", str(tmp_path / "c.png")] + size,
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "Resuming at sample 4 of 10" in r.stdout, r.stderr
+    assert np.abs(img(tmp_path / "c.png") - img(whole)).max() <= 1
+    # a checkpoint of another render is refused
+    r = subprocess.run([CLI, "--scene-file", scene, "-s", "10", "--checkpoint", ck, "-o", str(tmp_path / "d.png"), "--width", "240", "--height", "135", "--seed", "8"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "does not match" in r.stderr

@@ -519,3 +519,22 @@ def test_native_image_decoders_survive_damaged_files(tmp_path):
             except N.FireworkError:
                 outcomes["error"] += 1
         assert outcomes["error"] >= 10, (name, outcomes)      # every truncation is an error
+
+
+def test_native_checkpoint_format_round_trips(tmp_path):
+    from firework_b200.progressive import fwck_fingerprint, fwck_load, fwck_save
+    rng = np.random.default_rng(2)
+    sums = rng.random((9, 14, 3), dtype=np.float32)
+    f = str(tmp_path / "x.fwck")
+    fwck_save(f, sums, 37, 5, 0x1234567890ABCDEF)
+    got, done, seed, fp = fwck_load(f)
+    assert np.array_equal(got, sums) and (done, seed, fp) == (37, 5, 0x1234567890ABCDEF)
+    assert os.path.getsize(f) == 40 + sums.nbytes
+    p = params_for("conics", 240, 135, 10, seed=7)
+    a = fwck_fingerprint("scene text", p)
+    assert a == fwck_fingerprint("scene text", params_for("conics", 240, 135, 99, seed=7))        # the sample count is not part of it
+    assert a != fwck_fingerprint("scene text", params_for("conics", 240, 135, 10, seed=8))
+    assert a != fwck_fingerprint("scene text.", p)
+    open(f, "wb").write(b"FWCKPT01" + b"\0" * 10)
+    with pytest.raises(ValueError):
+        fwck_load(f)
