@@ -3,21 +3,9 @@
 // SplitMix64 stream with the same seed in its place, so both mirrors generate the same 485 spheres (the document is compared
 // byte for byte with the Python mirror's in tests/test_host.py).
 #include "common.hpp"
+#include "scene_rng.hpp"
 
 using namespace firework;
-
-struct SceneRng {   // stands in for tiny_rng::Rng (scenes.py SceneRng)
-    uint64_t state;
-    explicit SceneRng(uint64_t seed) : state(seed) {}
-    uint64_t next_u64() {
-        state += 0x9E3779B97F4A7C15ull;
-        uint64_t z = state;
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-        return z ^ (z >> 31);
-    }
-    float rand_f32() { return (float)((double)(next_u64() >> 40) * (1.0 / 16777216.0)); }
-};
 
 Scene random_scene(SceneRng& rand) {   // random_spheres.rs:14-67
     Scene scene = Scene::new_();

@@ -482,11 +482,14 @@ def test_cpp_api_mirror_serialises_the_examples_like_the_python_mirror(tmp_path)
     import subprocess
     from firework_b200 import scenes
     for name, make in (("cornell_box", scenes.cornell_box), ("earth", scenes.earth_scene), ("volume_test", scenes.volume_scene),
-                       ("random_spheres", lambda: scenes.random_scene(scenes.SceneRng(12345)))):
+                       ("random_spheres", lambda: scenes.random_scene(scenes.SceneRng(12345))),
+                       ("part2_all", lambda: scenes.final_scene(scenes.SceneRng(12345)))):
         exe = _build_example(name, tmp_path)
         r = subprocess.run([exe, "--yaml"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert r.stdout == make().to_yaml(), name
+        if name in ("random_spheres", "part2_all"):     # ... which is the committed scene file the benchmarks load
+            assert r.stdout == open(CONFIGS[name].path()).read(), name
         h = C.c_void_p()
         data = r.stdout.encode()
         assert N.lib().fw_scene_from_yaml(data, len(data), C.byref(h)) == 0      # and the native loader takes it
