@@ -9,7 +9,7 @@
  * `serde_yaml::to_string(&scene)` (src/scene.rs:18, src/serde_compat.rs) — that text is what
  * fw_scene_from_yaml takes.  INTEGRATION.md shows the Rust binding (`extern "C"` + build.rs) a
  * maintainer would add to call this from `Renderer::render`; include/firework.hpp is a C++ mirror of the crate's public
- * builder API on top of this header (examples/ restates five of the crate's examples with it).
+ * builder API on top of this header (examples/ restates seven of the crate's examples with it).
  *
  * Conventions: plain pointers and sizes; the caller owns every buffer it passes; the library owns
  * fw_scene until fw_scene_destroy; every call returns 0 on success or a negative fw_status, and

@@ -541,3 +541,19 @@ def test_native_checkpoint_format_round_trips(tmp_path):
     open(f, "wb").write(b"FWCKPT01" + b"\0" * 10)
     with pytest.raises(ValueError):
         fwck_load(f)
+
+
+def test_cpp_mesh_examples_reproduce_the_references_own_scene_dumps(tmp_path):
+    """examples/suzanne.rs and examples/teapot.rs write `serde_yaml::to_string(&scene)` to scenes/suzanne.yml / teapot.yml — the
+    files the reference commits.  The same examples restated in C++ (include/firework.hpp + the `add_obj` helper over
+    fw_obj_load) must produce a document that parses to exactly that: every vertex, normal, index, rotor component and material
+    (the two serialisers only differ in how many digits they print for an f32)."""
+    import subprocess
+    from firework_b200.scenes import SCENE_DIR
+    for name in ("suzanne", "teapot"):
+        exe = _build_example(name, tmp_path)
+        r = subprocess.run([exe, "--obj", os.path.join(SCENE_DIR, "assets", name + ".obj"), "--yaml"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert loads(r.stdout) == scene_doc(name), name
+    r = subprocess.run([exe, "--obj", str(tmp_path / "missing.obj"), "--yaml"], capture_output=True, text=True)
+    assert r.returncode == 1 and "add_obj" in r.stderr
