@@ -119,3 +119,22 @@ def test_checkpoints_move_between_the_native_and_the_python_driver(tmp_path):
     r = subprocess.run([CLI, "--scene-file", scene, "-s", "10", "--checkpoint", ck, "-o", str(tmp_path / "d.png"), "--width", "240", "--height", "135", "--seed", "8"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "does not match" in r.stderr
+
+
+def test_cpp_mesh_example_renders_the_committed_scene(tmp_path):
+    """examples/suzanne.cpp builds its scene from suzanne.obj through the C++ mirror; the reference's committed scenes/suzanne.yml is
+    the same document (tests/test_host.py), so both must render the same pixels."""
+    from PIL import Image
+    from conftest import native_scene, params_for
+    from test_host import _build_example
+    from firework_b200.scenes import SCENE_DIR
+    exe = _build_example("suzanne", tmp_path)
+    out = str(tmp_path / "suzanne.png")
+    r = subprocess.run([exe, "--obj", os.path.join(SCENE_DIR, "assets", "suzanne.obj"), "-s", "6", "--width", "160", "--height", "90", "--seed", "3", "-o", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ns = native_scene("suzanne")
+    p = params_for("suzanne", 160, 90, 6, seed=3)        # the example's camera (suzanne.rs:88-91), use_bvh(true)
+    want, _, _ = ns.render(p, want_sum=False)
+    ns.close()
+    assert np.array_equal(np.asarray(Image.open(out).convert("RGB")), want)
