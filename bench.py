@@ -390,6 +390,8 @@ def main():
             if pj:
                 lanes, ipc = pj.get("threads_per_inst_time_weighted"), pj.get("ipc_per_sm_time_weighted")
                 roof["issue_slots"] = {"lanes_of_32": lanes, "ipc_of_4": ipc, "useful_frac": (ipc / 4.0) * (lanes / 32.0) if lanes and ipc else None,
+                                       "fma_pipe_pct": pj.get("fma_pipe_pct_time_weighted"), "alu_pipe_pct": pj.get("alu_pipe_pct_time_weighted"),
+                                       "l1_hit_pct": pj.get("l1_hit_pct_time_weighted"), "registers": pj.get("registers"),
                                        "source": f"profiles/{PROFILE_TAG}_extend_traffic_{c.name}.json (ncu --set full of the extend launches of one batch)"}
             out["roofline"] = roof
             l2 = {"bound": "l2", "achieved": bytes_ray * prof["rays"] / ext_s / 1e9, "peak": peaks["l2_gbs"], "unit": "GB/s",
